@@ -1,0 +1,152 @@
+/*
+ * dfmdock_b200 -- C ABI of the B200-native DFMDock reverse-diffusion docking sampler.
+ *
+ * The reference (Graylab/DFMDock) is pure Python/PyTorch and has no FFI layer; its seam for this
+ * path is Python duck typing.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository root).  INTEGRATION.md shows
+ * the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DFM_E* code; nothing throws across the ABI;
+ *     dfm_last_error() returns a thread-local message for the last failure.
+ *   - all tensor arguments are DEVICE pointers (fp32 / int32, row-major, contiguous) unless a
+ *     parameter name ends in _host.  The caller owns every buffer passed in; the library only
+ *     owns what dfm_create / dfm_set_weight / dfm_set_complex allocate inside the context and
+ *     allocates nothing in dfm_score_forward / dfm_reverse_step / dfm_sample (the workspace is
+ *     handed in by the caller, sized by dfm_workspace_bytes).
+ *   - all work is stream-ordered on the cudaStream_t passed as `stream` (a void* here so that the
+ *     header needs no CUDA include); no entry point synchronises the device except dfm_create,
+ *     dfm_finalize_weights and dfm_destroy.
+ *   - one context per (device, stream); contexts are independent; a context is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with DFM_ECUDA.
+ */
+#ifndef DFMDOCK_B200_H_
+#define DFMDOCK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dfm_ctx dfm_ctx;
+
+enum {
+  DFM_OK = 0,
+  DFM_EINVAL = -1,    /* bad argument / shape mismatch */
+  DFM_ECUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+  DFM_ESTATE = -3,    /* call out of order (weights not finalised, no complex set, ...) */
+  DFM_ENOMEM = -4,    /* workspace too small */
+  DFM_EMISSING = -5   /* a required weight tensor was never supplied */
+};
+
+/* dfm_score_forward / dfm_sample flags */
+enum {
+  DFM_WANT_ENERGY = 1u << 0,   /* run the pair-energy head + clash count (final forward only in the sampler) */
+  DFM_PRECISION_FP32 = 1u << 1,/* fp32 FFMA kernels (parity mode); default = fp16-operand tcgen05 kernels, fp32 accumulate */
+  DFM_CLASH_FORCE = 1u << 2,   /* inference.py:358-361 soft-clash translation after every step */
+  DFM_NOISE_ANNEAL = 1u << 3,  /* noise_scale = t (inference_base.py:428-430) */
+  DFM_CENTRE_ALL_ATOMS = 1u << 4, /* rotate about the N/CA/C centroid (inference.py:224-245) instead of the CA centroid (inference_base.py:322-343) */
+  DFM_ODE = 1u << 5            /* probability-flow ODE branch of torch_reverse (so3_diffuser.py:366-367) */
+};
+
+/* Fixed architecture of the shipped checkpoints (configs/model/score_model_mlsb.yaml). */
+#define DFM_NODE_DIM 256
+#define DFM_EDGE_DIM 128
+#define DFM_INNER_DIM 128
+#define DFM_DEPTH 6
+#define DFM_KNN 20
+#define DFM_NSAMPLE 40
+#define DFM_EDGE_SLOTS 64 /* per-node stride of every [B, N, slot] edge array (60 used) */
+
+/* Replaces: Score_Model.load_from_checkpoint(...) -> Score_Net.__init__ (src/models/score_model_mlsb.py:22-59,
+ * src/models/score_net_mlsb.py:251-330).  Creates an empty context on CUDA device `device`. */
+int dfm_create(dfm_ctx** out, int device);
+
+/* Replaces: load_state_dict of one tensor.  `name` is the checkpoint key without the leading "net."
+ * (e.g. "network.EGNN_3.egcl.edge_mlp.0.weight"); `data` is a DEVICE fp32 pointer in nn.Linear [out, in]
+ * row-major layout; the tensor is copied.  Unknown names are stored and ignored. */
+int dfm_set_weight(dfm_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+
+/* Validates that all 104-10 hot-path tensors are present with the expected shapes, then builds the
+ * derived device tables: per-layer pair tables T_l = W1e_l * [spatial_embed | positional_embed]
+ * (SURVEY App. A.5), fp16 weight images in the tcgen05 shared-memory layout, folded biases.
+ * cut_off = hyper_parameters.model.cut_off (score_net_mlsb.py:264). Synchronises. */
+int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream);
+
+/* Replaces: the per-complex, pose-invariant part of Score_Net.forward: single_embed(x)
+ * (score_net_mlsb.py:365-366) and get_position_matrix (inference_base.py:230-244).
+ * rec_x [R, x_dim], lig_x [L, x_dim] (x_dim = 1301), rec_pos [R,3,3] (N, CA, C; Angstrom).
+ * sym = value of positional channel 66 for 67-wide checkpoints, ignored otherwise. */
+int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const float* rec_x, const float* lig_x,
+                    const float* rec_pos, float sym, void* stream);
+
+/* Bytes of scratch dfm_score_forward / dfm_sample need for B simultaneous trajectories of the current complex. */
+size_t dfm_workspace_bytes(const dfm_ctx* ctx, int B);
+
+/* Number of edges per node for the current complex: min(N, 60) (score_net_mlsb.py:89-94). */
+int dfm_edges_per_node(const dfm_ctx* ctx);
+
+/* Replaces: Score_Model.forward(batch) (src/models/score_model_mlsb.py:61-63 -> score_net_mlsb.py:343-425)
+ * for B independent ligand poses of the current complex.
+ *   lig_pos  [B, L, 3, 3]   current ligand backbone poses
+ *   t        [B]            diffusion times
+ *   edges    [B, N, K] int32 or NULL  injected neighbour table (parity mode), K = dfm_edges_per_node
+ *   exp_noise[B, N, N-20] or NULL     injected Exp(1) draws in torch.multinomial's compacted order (parity mode)
+ *   seed, stream_base, forward_index  Philox key/counter when neither is injected: trajectory b uses
+ *                                     subsequence stream_base + b, so results do not depend on sharding
+ * Outputs (any may be NULL): tr_score [B,3], rot_score [B,3], f [B,L,3], energy [B], num_clashes [B] int32
+ * (energy / num_clashes are only written with DFM_WANT_ENERGY), edges_out [B,N,K] int32. */
+int dfm_score_forward(dfm_ctx* ctx, int B, const float* lig_pos, const float* t, const int32_t* edges,
+                      const float* exp_noise, uint64_t seed, uint64_t stream_base, uint32_t forward_index,
+                      uint32_t flags, float* tr_score, float* rot_score, float* f, float* energy,
+                      int32_t* num_clashes, int32_t* edges_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Replaces: one body of the reverse loop after the forward (inference_base.py:439-461):
+ * so3/r3 torch_reverse (so3_diffuser.py:344-369, r3_diffuser.py:40-55), modify_coords (:342-352),
+ * tr_update/rot_compose accumulation (:455-456, :311-316) and, with DFM_CLASH_FORCE, get_clash_force (:366-384).
+ *   g_rot, g_tr     diffusion coefficients g(t) (computed by the host in fp64 like the reference, passed as float)
+ *   dt              step size (time_steps[0]-time_steps[1])
+ *   ns_rot, ns_tr   noise scales for this step
+ *   z [B, 2, 3] or NULL   injected N(0,1) draws (z[b,0]=rotation, z[b,1]=translation); NULL -> Philox
+ * In/out: lig_pos [B,L,3,3], rot_update [B,3] (axis-angle), tr_update [B,3]. */
+int dfm_reverse_step(dfm_ctx* ctx, int B, float* lig_pos, float* rot_update, float* tr_update,
+                     const float* tr_score, const float* rot_score, float g_rot, float g_tr, float dt,
+                     float ns_rot, float ns_tr, const float* z, uint64_t seed, uint64_t stream_base,
+                     uint32_t step_index, uint32_t flags, void* stream);
+
+/* Replaces: randomize_pose (inference_base.py:318-340 / inference.py:220-242) for B trajectories.
+ *   lig_pos0 [L,3,3]  input ligand pose;  quat0 [B,4] / tr0 [B,3] or NULL: injected unnormalised N(0,1)
+ *   quaternion draws (scipy Rotation.random) and N(0, 30^2) translation draws; NULL -> Philox.
+ * Out: lig_pos [B,L,3,3], rot_update [B,3], tr_update [B,3]. */
+int dfm_randomize_pose(dfm_ctx* ctx, int B, const float* lig_pos0, const float* quat0, const float* tr0,
+                       uint64_t seed, uint64_t stream_base, uint32_t flags, float* lig_pos,
+                       float* rot_update, float* tr_update, void* stream);
+
+/* Replaces: Euler_Maruyama_sampler (inference_base.py:390-468) for B trajectories in lock step plus the
+ * serial per-trajectory driver loop (inference_base.py:644-657): randomize_pose, num_steps x
+ * {forward, reverse step}, final forward with energy.  All noise from Philox (seed, stream_base + b).
+ * Out: lig_pos [B,L,3,3], rot_update [B,3], tr_update [B,3], energy [B], num_clashes [B] int32. */
+int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_steps, float eps, float tr_noise_scale,
+               float rot_noise_scale, uint32_t flags, uint64_t seed, uint64_t stream_base, float* lig_pos,
+               float* rot_update, float* tr_update, float* energy, int32_t* num_clashes, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* Number of kernels the library launched on behalf of this context since creation (bench.py "gpu_launches"). */
+uint64_t dfm_launch_count(const dfm_ctx* ctx);
+
+/* Debug / parity taps: copy an internal fp32 buffer of the last dfm_score_forward into `out`.
+ * which: 0 = node features h after the last layer [B,N,256], 1 = packed pair-feature bins [B,N,64] (as int32),
+ * 2 = radial [B,N,64].  Returns the element count or a negative error. */
+int64_t dfm_debug_read(dfm_ctx* ctx, int which, void* out, size_t out_bytes, void* workspace, void* stream);
+
+const char* dfm_last_error(void);
+const char* dfm_version(void);
+void dfm_destroy(dfm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFMDOCK_B200_H_ */
