@@ -1,0 +1,460 @@
+// C ABI (include/dfmdock_b200.h): context, weight repacking, the forward pass schedule and the sampler loop.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+int dfm_upload_bin_edges();
+int launch_randomize_pose(dfm_ctx*, int, const float*, const float*, const float*, uint64_t, uint64_t, uint32_t, float*,
+                          float*, float*, cudaStream_t);
+int launch_reverse_step(dfm_ctx*, int, float*, float*, float*, const float*, const float*, float, float, float, float,
+                        float, const float*, uint64_t, uint64_t, uint32_t, uint32_t, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+void dfm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* dfm_last_error(void) { return g_err; }
+extern "C" const char* dfm_version(void) { return "dfmdock_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base) {
+  Workspace w{};
+  const size_t N = ctx->N, L = ctx->L, R = ctx->R, b = B;
+  size_t off = 0;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  w.centre = (float*)take(b * 4 * 4);
+  w.pos = (float*)take(b * N * 9 * 4);
+  w.cb = (float*)take(b * N * 4 * 4);
+  w.nbr = (int32_t*)take(b * N * SLOTS * 4);
+  w.feat = (uint32_t*)take(b * N * SLOTS * 4);
+  w.radial = (float*)take(b * N * SLOTS * 4);
+  w.h = (float*)take(b * N * H * 4);
+  w.A = (float*)take(b * N * H * 4);
+  w.Bm = (float*)take(b * N * H * 4);
+  w.agg = (float*)take(b * N * H * 4);
+  w.z = (float*)take(b * N * H * 4);
+  w.y = (float*)take(b * N * H * 4);
+  w.gstat = (float*)take(b * 2 * H * 4);
+  w.mstar = (__half*)take(b * L * SLOTS * H * 2);
+  w.fbuf = (float*)take(b * L * 4 * 4);
+  w.esum = (float*)take(b * R * 4 * 4);
+  w.tsc = (float*)take(b * 8 * 4);
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t dfm_workspace_bytes(const dfm_ctx* ctx, int B) {
+  if (!ctx || !ctx->has_complex || B <= 0) return 0;
+  return carve_workspace(ctx, B, nullptr).bytes;
+}
+extern "C" int dfm_edges_per_node(const dfm_ctx* ctx) { return ctx ? ctx->K : 0; }
+extern "C" uint64_t dfm_launch_count(const dfm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dfm_create(dfm_ctx** out, int device) {
+  if (!out) { dfm_set_error("dfm_create: null out"); return DFM_EINVAL; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    dfm_set_error("dfm_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return DFM_ECUDA;
+  }
+  if (device < 0 || device >= count) { dfm_set_error("dfm_create: bad device %d", device); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    dfm_set_error("dfm_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return DFM_ECUDA;
+  }
+  dfm_ctx* c = new dfm_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (dfm_upload_bin_edges() != 0) {
+    delete c;
+    dfm_set_error("dfm_create: cannot upload bin edges");
+    return DFM_ECUDA;
+  }
+  *out = c;
+  return DFM_OK;
+}
+
+extern "C" void dfm_destroy(dfm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->w) cudaFree(kv.second.d);
+  for (void* p : ctx->owned) cudaFree(p);
+  cudaFree(ctx->h0);
+  cudaFree(ctx->rec_pos);
+  delete ctx;
+}
+
+extern "C" int dfm_set_weight(dfm_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!ctx || !name || !data || ndim < 0 || ndim > 4) { dfm_set_error("dfm_set_weight: bad argument"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  WTensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+  CUDA_TRY(cudaMalloc(&t.d, sizeof(float) * (size_t)(t.numel > 0 ? t.numel : 1)));
+  CUDA_TRY(cudaMemcpy(t.d, data, sizeof(float) * (size_t)t.numel, cudaMemcpyDeviceToDevice));
+  auto it = ctx->w.find(name);
+  if (it != ctx->w.end()) { cudaFree(it->second.d); ctx->w.erase(it); }
+  ctx->w[name] = t;
+  ctx->finalized = false;
+  return DFM_OK;
+}
+
+static int need(dfm_ctx* ctx, const std::string& name, std::vector<int64_t> shape, const float** out) {
+  auto it = ctx->w.find(name);
+  if (it == ctx->w.end()) { dfm_set_error("missing weight '%s'", name.c_str()); return DFM_EMISSING; }
+  if (it->second.shape != shape) {
+    std::string got, want;
+    for (auto v : it->second.shape) got += std::to_string(v) + ",";
+    for (auto v : shape) want += std::to_string(v) + ",";
+    dfm_set_error("weight '%s' has shape [%s], expected [%s]", name.c_str(), got.c_str(), want.c_str());
+    return DFM_EINVAL;
+  }
+  *out = it->second.d;
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(dfm_ctx* ctx, T** p, size_t n) {
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  ctx->owned.push_back(*p);
+  return 0;
+}
+
+extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
+  if (!ctx) { dfm_set_error("null ctx"); return DFM_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc;
+#define NEED(name, ...) if ((rc = need(ctx, name, __VA_ARGS__, &tmp)) != 0) return rc
+  const float* tmp = nullptr;
+  auto pe = ctx->w.find("positional_embed.weight");
+  if (pe == ctx->w.end() || pe->second.shape.size() != 2) { dfm_set_error("missing weight 'positional_embed.weight'"); return DFM_EMISSING; }
+  ctx->P = (int)pe->second.shape[1];
+  if (ctx->P != 66 && ctx->P != 67) { dfm_set_error("positional_embed width %d not supported (66 or 67)", ctx->P); return DFM_EINVAL; }
+  auto se = ctx->w.find("single_embed.weight");
+  if (se == ctx->w.end() || se->second.shape.size() != 2 || se->second.shape[0] != H) { dfm_set_error("missing/invalid 'single_embed.weight'"); return DFM_EMISSING; }
+  ctx->x_dim = (int)se->second.shape[1];
+  NEED("spatial_embed.weight", {ED, NSPATIAL});
+  NEED("positional_embed.weight", {ED, ctx->P});
+  for (void* p : ctx->owned) cudaFree(p);
+  ctx->owned.clear();
+  for (int l = 0; l < DFM_DEPTH; ++l) {
+    LayerW& w = ctx->layer[l];
+    const std::string pre = "network.EGNN_" + std::to_string(l) + ".egcl.";
+    NEED(pre + "edge_mlp.0.weight", {H, 2 * H + 1 + ED}); w.W1 = tmp;
+    NEED(pre + "edge_mlp.0.bias", {H}); w.b1 = tmp;
+    NEED(pre + "edge_mlp.2.weight", {H, H}); w.W2 = tmp;
+    NEED(pre + "edge_mlp.2.bias", {H}); w.b2 = tmp;
+    NEED(pre + "node_mlp.0.weight", {H, 2 * H}); w.W3 = tmp;
+    NEED(pre + "node_mlp.0.bias", {H}); w.b3 = tmp;
+    NEED(pre + "node_mlp.1.weight", {H}); w.gn_w = tmp;
+    NEED(pre + "node_mlp.1.bias", {H}); w.gn_b = tmp;
+    NEED(pre + "node_mlp.1.mean_scale", {H}); w.gn_ms = tmp;
+    NEED(pre + "node_mlp.3.weight", {H, H}); w.W4 = tmp;
+    NEED(pre + "node_mlp.3.bias", {H}); w.b4 = tmp;
+    NEED(pre + "att_mlp.0.weight", {1, H}); w.wa = tmp;
+    NEED(pre + "att_mlp.0.bias", {1}); w.ba = tmp;
+    w.Wc1 = w.bc1 = w.wc2 = nullptr;
+    if (l == DFM_DEPTH - 1) {
+      NEED(pre + "coord_mlp.0.weight", {H, H}); w.Wc1 = tmp;
+      NEED(pre + "coord_mlp.0.bias", {H}); w.bc1 = tmp;
+      NEED(pre + "coord_mlp.2.weight", {1, H}); w.wc2 = tmp;
+    }
+    const size_t trows = NSPATIAL + ctx->P;
+    if ((rc = dev_alloc(ctx, &w.T32, trows * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.T16, trows * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.w1r, H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.b1eff, H))) return rc;
+    __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1};
+    for (auto pp : imgs) if ((rc = dev_alloc(ctx, pp, (size_t)H * H))) return rc;
+    if ((rc = launch_pair_table(ctx, l, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W1, 641, 0, 1.f, w.img_W1s, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W1, 641, 256, 1.f, w.img_W1d, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W2, 256, 0, S_UNSCALE, w.img_W2, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W3, 512, 0, 1.f, w.img_W3h, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W3, 512, 256, AGG_UNSCALE, w.img_W3a, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W4, 256, 0, 1.f, w.img_W4, s))) return rc;
+    if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, S_UNSCALE, w.img_Wc1, s))) return rc;
+  }
+  NEED("to_energy.0.weight", {H, 2 * H}); ctx->We = tmp;
+  NEED("to_energy.1.weight", {H}); ctx->e_ln_w = tmp;
+  NEED("to_energy.1.bias", {H}); ctx->e_ln_b = tmp;
+  NEED("to_energy.3.weight", {1, H}); ctx->e_w = tmp;
+  if ((rc = dev_alloc(ctx, &ctx->img_WeR, (size_t)H * H))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->img_WeL, (size_t)H * H))) return rc;
+  if ((rc = launch_image_pack(ctx, ctx->We, 512, 0, 1.f, ctx->img_WeR, s))) return rc;
+  if ((rc = launch_image_pack(ctx, ctx->We, 512, 256, 1.f, ctx->img_WeL, s))) return rc;
+  NEED("t_embed.0.W", {DFM_INNER_DIM / 2}); ctx->t_W = tmp;
+  NEED("t_embed.1.weight", {DFM_INNER_DIM, DFM_INNER_DIM}); ctx->t_lin = tmp;
+  const char* sc[2] = {"tr_scale", "rot_scale"};
+  for (int q = 0; q < 2; ++q) {
+    NEED(std::string(sc[q]) + ".0.weight", {DFM_INNER_DIM, DFM_INNER_DIM + 1}); ctx->sc_W1[q] = tmp;
+    NEED(std::string(sc[q]) + ".1.weight", {DFM_INNER_DIM}); ctx->sc_lnw[q] = tmp;
+    NEED(std::string(sc[q]) + ".1.bias", {DFM_INNER_DIM}); ctx->sc_lnb[q] = tmp;
+    NEED(std::string(sc[q]) + ".4.weight", {1, DFM_INNER_DIM}); ctx->sc_w2[q] = tmp;
+  }
+#undef NEED
+  ctx->cut_off = cut_off;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  ctx->finalized = true;
+  ctx->has_complex = false;
+  return DFM_OK;
+}
+
+__global__ void k_b1eff(const float* __restrict__ b1, const float* __restrict__ T32, int P, float sym, float* __restrict__ out) {
+  const int c = threadIdx.x;
+  float v = b1[c];
+  if (P == 67) v = fmaf(sym, T32[(size_t)(NSPATIAL + 66) * H + c], v);
+  out[c] = v;
+}
+
+extern "C" int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const float* rec_x, const float* lig_x,
+                               const float* rec_pos, float sym, void* stream) {
+  if (!ctx || !ctx->finalized) { dfm_set_error("dfm_set_complex: weights not finalised"); return DFM_ESTATE; }
+  if (R <= 0 || L <= 0 || !rec_x || !lig_x || !rec_pos) { dfm_set_error("dfm_set_complex: bad argument"); return DFM_EINVAL; }
+  if (x_dim != ctx->x_dim) { dfm_set_error("dfm_set_complex: x_dim %d != single_embed width %d", x_dim, ctx->x_dim); return DFM_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->R = R; ctx->L = L; ctx->N = R + L;
+  const int N = ctx->N;
+  // score_net_mlsb.py:89-94
+  ctx->knn = N < DFM_KNN ? N : DFM_KNN;
+  ctx->ns = N < DFM_KNN ? 0 : (N < DFM_KNN + DFM_NSAMPLE ? N - DFM_KNN : DFM_NSAMPLE);
+  ctx->K = ctx->knn + ctx->ns;
+  ctx->sym = sym;
+  if ((size_t)N * H > ctx->h0_cap) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(ctx->h0);
+    CUDA_TRY(cudaMalloc(&ctx->h0, sizeof(float) * (size_t)N * H));
+    ctx->h0_cap = (size_t)N * H;
+  }
+  if ((size_t)R * 9 > ctx->rec_cap) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(ctx->rec_pos);
+    CUDA_TRY(cudaMalloc(&ctx->rec_pos, sizeof(float) * (size_t)R * 9));
+    ctx->rec_cap = (size_t)R * 9;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->rec_pos, rec_pos, sizeof(float) * (size_t)R * 9, cudaMemcpyDeviceToDevice, s));
+  int rc = launch_single_embed(ctx, rec_x, lig_x, s);
+  if (rc) return rc;
+  for (int l = 0; l < DFM_DEPTH; ++l) {
+    k_b1eff<<<1, 256, 0, s>>>(ctx->layer[l].b1, ctx->layer[l].T32, ctx->P, sym, ctx->layer[l].b1eff);
+    LAUNCH_CHECK(ctx);
+  }
+  ctx->has_complex = true;
+  return DFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int linear(dfm_ctx* ctx, bool fp32, const LinearArgs& a, cudaStream_t s) {
+  return fp32 ? launch_linear_simt(ctx, a, s) : launch_linear_tc(ctx, a, s);
+}
+
+static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* t, const int32_t* edges,
+                        const float* exp_noise, uint64_t seed, uint64_t stream_base, uint32_t fwd_index, uint32_t flags,
+                        float* tr_score, float* rot_score, float* f, float* energy, int32_t* clashes, int32_t* edges_out,
+                        Workspace& ws, cudaStream_t s) {
+  const bool fp32 = (flags & DFM_PRECISION_FP32) != 0;
+  const bool want_energy = (flags & DFM_WANT_ENERGY) != 0;
+  const int N = ctx->N, M = B * N;
+  int rc;
+  if ((rc = launch_prepare(ctx, B, lig_pos, ws, s))) return rc;
+  if ((rc = launch_graph(ctx, B, edges, exp_noise, seed, stream_base, fwd_index, ws, s))) return rc;
+  if (edges_out) {
+    CUDA_TRY(cudaMemcpy2DAsync(edges_out, sizeof(int32_t) * ctx->K, ws.nbr, sizeof(int32_t) * SLOTS,
+                               sizeof(int32_t) * ctx->K, (size_t)M, cudaMemcpyDeviceToDevice, s));
+  }
+  if ((rc = launch_broadcast_h0(ctx, B, ws, s))) return rc;
+  for (int l = 0; l < DFM_DEPTH; ++l) {
+    const LayerW& w = ctx->layer[l];
+    const bool last = l == DFM_DEPTH - 1;
+    LinearArgs la{};
+    la.A = ws.h; la.a_scale = 1.f; la.M = M;
+    // A = W1s h + b1
+    la.W32 = w.W1; la.ldw = 641; la.w_col0 = 0; la.Wimg = w.img_W1s; la.bias = w.b1eff; la.add = nullptr;
+    la.out = ws.A; la.out16 = nullptr;
+    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    // Bm = W1d h
+    la.w_col0 = 256; la.Wimg = w.img_W1d; la.bias = nullptr;
+    if (fp32) { la.out = ws.Bm; la.out16 = nullptr; } else { la.out = nullptr; la.out16 = reinterpret_cast<__half*>(ws.Bm); }
+    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    EdgeArgs ea{};
+    ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
+    ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
+    ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
+    if (fp32) {
+      if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
+    } else {
+      if ((rc = launch_edge_tc(ctx, ea, s))) return rc;
+      if (last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
+    }
+    if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
+    // z = W3h h + b3 + W3a agg
+    la.A = ws.h; la.a_scale = 1.f; la.W32 = w.W3; la.ldw = 512; la.w_col0 = 0; la.Wimg = w.img_W3h; la.bias = w.b3;
+    la.add = nullptr; la.out = ws.z; la.out16 = nullptr;
+    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    la.A = ws.agg; la.a_scale = fp32 ? 1.f : AGG_SCALE; la.w_col0 = 256; la.Wimg = w.img_W3a; la.bias = nullptr;
+    la.add = ws.z;
+    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    if ((rc = launch_graphnorm_silu(ctx, B, l, ws, s))) return rc;
+    // h += W4 y + b4
+    la.A = ws.y; la.a_scale = 1.f; la.W32 = w.W4; la.ldw = 256; la.w_col0 = 0; la.Wimg = w.img_W4; la.bias = w.b4;
+    la.add = ws.h; la.out = ws.h;
+    if ((rc = linear(ctx, fp32, la, s))) return rc;
+  }
+  float* trs = tr_score ? tr_score : ws.tsc;
+  float* rots = rot_score ? rot_score : ws.tsc + (size_t)B * 4;
+  if ((rc = launch_force_head(ctx, B, t, ws, trs, rots, f, s))) return rc;
+  if (want_energy && (rc = launch_energy(ctx, B, fp32, ws, energy, clashes, s))) return rc;
+  return 0;
+}
+
+static int check_ws(dfm_ctx* ctx, int B, void* workspace, size_t bytes, Workspace* ws) {
+  if (!ctx || !ctx->has_complex) { dfm_set_error("no complex set"); return DFM_ESTATE; }
+  if (B <= 0) { dfm_set_error("B must be positive"); return DFM_EINVAL; }
+  *ws = carve_workspace(ctx, B, workspace);
+  if (!workspace || bytes < ws->bytes) {
+    dfm_set_error("workspace too small: %zu < %zu bytes", bytes, ws->bytes);
+    return DFM_ENOMEM;
+  }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) { dfm_set_error("workspace must be 256-byte aligned"); return DFM_EINVAL; }
+  return 0;
+}
+
+extern "C" int dfm_score_forward(dfm_ctx* ctx, int B, const float* lig_pos, const float* t, const int32_t* edges,
+                                 const float* exp_noise, uint64_t seed, uint64_t stream_base, uint32_t forward_index,
+                                 uint32_t flags, float* tr_score, float* rot_score, float* f, float* energy,
+                                 int32_t* num_clashes, int32_t* edges_out, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  Workspace ws;
+  int rc = check_ws(ctx, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (!lig_pos || !t) { dfm_set_error("dfm_score_forward: lig_pos and t are required"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return forward_impl(ctx, B, lig_pos, t, edges, exp_noise, seed, stream_base, forward_index, flags, tr_score, rot_score,
+                      f, energy, num_clashes, edges_out, ws, (cudaStream_t)stream);
+}
+
+extern "C" int dfm_reverse_step(dfm_ctx* ctx, int B, float* lig_pos, float* rot_update, float* tr_update,
+                                const float* tr_score, const float* rot_score, float g_rot, float g_tr, float dt,
+                                float ns_rot, float ns_tr, const float* z, uint64_t seed, uint64_t stream_base,
+                                uint32_t step_index, uint32_t flags, void* stream) {
+  if (!ctx || !ctx->has_complex) { dfm_set_error("no complex set"); return DFM_ESTATE; }
+  if (B <= 0 || !lig_pos || !rot_update || !tr_update || !tr_score || !rot_score) { dfm_set_error("dfm_reverse_step: bad argument"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return launch_reverse_step(ctx, B, lig_pos, rot_update, tr_update, tr_score, rot_score, g_rot, g_tr, dt, ns_rot, ns_tr, z,
+                             seed, stream_base, step_index, flags, (cudaStream_t)stream);
+}
+
+extern "C" int dfm_randomize_pose(dfm_ctx* ctx, int B, const float* lig_pos0, const float* rot0, const float* tr0,
+                                  uint64_t seed, uint64_t stream_base, uint32_t flags, float* lig_pos, float* rot_update,
+                                  float* tr_update, void* stream) {
+  if (!ctx || !ctx->has_complex) { dfm_set_error("no complex set"); return DFM_ESTATE; }
+  if (B <= 0 || !lig_pos0 || !lig_pos || !rot_update || !tr_update) { dfm_set_error("dfm_randomize_pose: bad argument"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return launch_randomize_pose(ctx, B, lig_pos0, rot0, tr0, seed, stream_base, flags, lig_pos, rot_update, tr_update,
+                               (cudaStream_t)stream);
+}
+
+// host-side schedules, fp64 like the reference's numpy (so3_diffuser.py:210-227, r3_diffuser.py:20-24)
+static double so3_g(double t) {
+  const double lo = 0.1, hi = 1.5;
+  const double sg = log(t * exp(hi) + (1 - t) * exp(lo));
+  return sqrt(2 * (exp(hi) - exp(lo)) * sg / exp(sg));
+}
+static double r3_g(double t) {
+  const double lo = 0.1, hi = 30.0;
+  return lo * pow(hi / lo, t) * sqrt(2 * (log(hi) - log(lo)));
+}
+
+__global__ void k_fill(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_steps, float eps, float tr_noise_scale,
+                          float rot_noise_scale, uint32_t flags, uint64_t seed, uint64_t stream_base, float* lig_pos,
+                          float* rot_update, float* tr_update, float* energy, int32_t* num_clashes, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  int rc = check_ws(ctx, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (!lig_pos0 || !lig_pos || !rot_update || !tr_update || num_steps < 2) { dfm_set_error("dfm_sample: bad argument"); return DFM_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if ((rc = launch_randomize_pose(ctx, B, lig_pos0, nullptr, nullptr, seed, stream_base, flags, lig_pos, rot_update, tr_update, s))) return rc;
+  // torch.linspace(1, eps, S) in fp32 and dt = ts[0] - ts[1]  (inference_base.py:404-405)
+  std::vector<float> ts(num_steps);
+  {
+    const float step = (eps - 1.0f) / (float)(num_steps - 1);
+    for (int i = 0; i < num_steps; ++i)
+      ts[i] = (i < num_steps / 2) ? fmaf(step, (float)i, 1.0f) : fmaf(-step, (float)(num_steps - 1 - i), eps);
+  }
+  const float dt = ts[0] - ts[1];
+  float* tbuf = ws.tsc + (size_t)B * 7;   // [B] time values live in the tail of the scratch block
+  float* trs = ws.tsc;
+  float* rots = ws.tsc + (size_t)B * 4;
+  const uint32_t fflags = flags & DFM_PRECISION_FP32;
+  for (int i = 0; i < num_steps; ++i) {
+    const bool last = i == num_steps - 1;
+    k_fill<<<(B + 255) / 256, 256, 0, s>>>(tbuf, ts[i], B);
+    LAUNCH_CHECK(ctx);
+    if ((rc = forward_impl(ctx, B, lig_pos, tbuf, nullptr, nullptr, seed, stream_base, (uint32_t)i, fflags, trs, rots,
+                           nullptr, nullptr, nullptr, nullptr, ws, s))) return rc;
+    float ns_tr, ns_rot;
+    if (flags & DFM_NOISE_ANNEAL) ns_tr = ns_rot = ts[i];
+    else if (last) ns_tr = ns_rot = 0.f;
+    else { ns_tr = tr_noise_scale; ns_rot = rot_noise_scale; }
+    if ((rc = launch_reverse_step(ctx, B, lig_pos, rot_update, tr_update, trs, rots, (float)so3_g((double)ts[i]),
+                                  (float)r3_g((double)ts[i]), dt, ns_rot, ns_tr, nullptr, seed, stream_base, (uint32_t)i,
+                                  flags, s))) return rc;
+    if (last) {
+      if ((rc = forward_impl(ctx, B, lig_pos, tbuf, nullptr, nullptr, seed, stream_base, (uint32_t)num_steps,
+                             fflags | DFM_WANT_ENERGY, trs, rots, nullptr, energy, num_clashes, nullptr, ws, s))) return rc;
+    }
+  }
+  return DFM_OK;
+}
+
+extern "C" int64_t dfm_debug_read(dfm_ctx* ctx, int B, int which, void* out, size_t out_bytes, void* workspace,
+                                  void* stream) {
+  if (!ctx || !ctx->has_complex || !out || !workspace || B <= 0) { dfm_set_error("dfm_debug_read: bad argument"); return DFM_EINVAL; }
+  Workspace ws = carve_workspace(ctx, B, workspace);
+  const void* src = nullptr;
+  size_t n = 0, esz = 4;
+  switch (which) {
+    case 0: src = ws.h; n = (size_t)B * ctx->N * H; break;
+    case 1: src = ws.feat; n = (size_t)B * ctx->N * SLOTS; break;
+    case 2: src = ws.radial; n = (size_t)B * ctx->N * SLOTS; break;
+    case 3: src = ws.nbr; n = (size_t)B * ctx->N * SLOTS; break;
+    case 4: src = ws.agg; n = (size_t)B * ctx->N * H; break;
+    case 5: src = ws.A; n = (size_t)B * ctx->N * H; break;
+    case 6: src = ws.fbuf; n = (size_t)B * ctx->L * 4; break;
+    default: dfm_set_error("dfm_debug_read: unknown buffer %d", which); return DFM_EINVAL;
+  }
+  if (out_bytes < n * esz) { dfm_set_error("dfm_debug_read: out too small"); return DFM_ENOMEM; }
+  if (cudaMemcpyAsync(out, src, n * esz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) {
+    dfm_set_error("dfm_debug_read: copy failed");
+    return DFM_ECUDA;
+  }
+  return (int64_t)n;
+}

@@ -1,0 +1,229 @@
+// Shared declarations for the dfmdock_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dfmdock_b200.h"
+
+#define H DFM_NODE_DIM          // 256 node features
+#define ED DFM_EDGE_DIM         // 128 pair-embedding features
+#define SLOTS DFM_EDGE_SLOTS    // 64 edge slots per node (60 used)
+#define NSPATIAL 100            // 40 dist + 24 omega + 24 theta + 12 phi one-hot rows
+#define NRELPOS 66
+
+// fp16 operand scaling (exact powers of two, undone in the weight images):
+//   S = SiLU(u) and m* are stored as value * 2^-4, agg as value * 2^-6 (observed |agg| up to 4.4e4).
+#define S_SCALE 0.0625f
+#define S_UNSCALE 16.0f
+#define AGG_SCALE 0.015625f
+#define AGG_UNSCALE 64.0f
+
+void dfm_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      dfm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+      return DFM_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      dfm_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return DFM_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+struct WTensor {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+// Per-layer device pointers (fp32 originals are views into the WTensor copies).
+struct LayerW {
+  const float* W1;      // edge_mlp.0.weight [256, 641] = [W1s | W1d | w1r | W1e]
+  const float* b1;      // [256]
+  const float* W2;      // edge_mlp.2.weight [256,256]
+  const float* b2;
+  const float* W3;      // node_mlp.0.weight [256,512] = [W3h | W3a]
+  const float* b3;
+  const float* gn_w;    // GraphNorm weight / bias / mean_scale
+  const float* gn_b;
+  const float* gn_ms;
+  const float* W4;      // node_mlp.3.weight
+  const float* b4;
+  const float* wa;      // att_mlp.0.weight [256]
+  const float* ba;      // [1]
+  const float* Wc1;     // coord_mlp.0 (last layer only)
+  const float* bc1;
+  const float* wc2;     // coord_mlp.2.weight [256]
+  // derived (owned)
+  float* T32;           // [100+P, 256] pair table, fp32
+  __half* T16;          // same, fp16
+  float* w1r;           // [256] column 512 of W1, contiguous
+  float* b1eff;         // [256] b1 + sym * T[166] (set per complex)
+  __half* img_W1s;      // fp16 SW128 images [4 kblk][256 rows][64]
+  __half* img_W1d;
+  __half* img_W2;       // x 2^4
+  __half* img_W3h;
+  __half* img_W3a;      // x 2^6
+  __half* img_W4;
+  __half* img_Wc1;      // x 2^4
+};
+
+struct dfm_ctx {
+  int device = 0;
+  std::map<std::string, WTensor> w;
+  bool finalized = false;
+  int P = 0;            // positional_embed width (66 or 67)
+  int x_dim = 0;
+  float cut_off = 20.f;
+  LayerW layer[DFM_DEPTH];
+  // heads
+  const float* We = nullptr;      // to_energy.0.weight [256,512]
+  const float* e_ln_w = nullptr;
+  const float* e_ln_b = nullptr;
+  const float* e_w = nullptr;     // to_energy.3.weight [256]
+  __half* img_WeR = nullptr;
+  __half* img_WeL = nullptr;
+  const float* t_W = nullptr;     // t_embed.0.W [64]
+  const float* t_lin = nullptr;   // t_embed.1.weight [128,128]
+  const float* sc_W1[2] = {nullptr, nullptr};  // tr_scale / rot_scale .0.weight [128,129]
+  const float* sc_lnw[2] = {nullptr, nullptr};
+  const float* sc_lnb[2] = {nullptr, nullptr};
+  const float* sc_w2[2] = {nullptr, nullptr};  // .4.weight [128]
+  // complex
+  bool has_complex = false;
+  int R = 0, L = 0, N = 0, K = 0, knn = 0, ns = 0;
+  float sym = 0.f;
+  float* h0 = nullptr;        // [N,256]
+  float* rec_pos = nullptr;   // [R,3,3]
+  size_t h0_cap = 0, rec_cap = 0;
+  uint64_t launches = 0;
+  int num_sms = 148;
+  std::vector<void*> owned;   // cudaMalloc'd derived buffers
+};
+
+// Workspace carve-up for B trajectories (all offsets 256-byte aligned).
+struct Workspace {
+  float* centre;     // [B,4]
+  float* pos;        // [B,N,3,3] centred N/CA/C
+  float* cb;         // [B,N,4]   virtual CB (padded)
+  int32_t* nbr;      // [B,N,64]
+  uint32_t* feat;    // [B,N,64]  packed bins: d | o<<6 | t<<11 | p<<16 | rp<<20
+  float* radial;     // [B,N,64]
+  float* h;          // [B,N,256]
+  float* A;          // [B,N,256]
+  float* Bm;         // [B,N,256] fp32 (simt) or fp16 in the first half (tc)
+  float* agg;        // [B,N,256]
+  float* z;          // [B,N,256]
+  float* y;          // [B,N,256]
+  float* gstat;      // [B,2,256] GraphNorm mean / rstd
+  __half* mstar;     // [B,L,64,256] fp16 * 2^-4 (tc path, last layer)
+  float* fbuf;       // [B,L,4]
+  float* esum;       // [B,R,2]
+  float* tsc;        // [B,8] tr_score(3) rot_score(3) scratch when the caller passes NULL
+  size_t bytes;
+};
+
+Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base);
+
+// ---- kernels (launchers) -----------------------------------------------------------------------
+struct LinearArgs {
+  const float* A;       // [M, 256] fp32 activations (row stride 256)
+  float a_scale;        // applied before the fp16 conversion in the tc path (1 = none)
+  const float* W32;     // fp32 weight, row-major [256, ldw], first column = w_col0
+  int ldw;
+  int w_col0;
+  const __half* Wimg;   // fp16 image (already multiplied by 1/a_scale)
+  const float* bias;    // [256] or null
+  const float* add;     // [M,256] or null; out = add + A*W^T + bias  (may alias out)
+  float* out;           // [M,256] fp32 or null
+  __half* out16;        // [M,256] fp16 or null
+  int M;
+};
+int launch_linear_simt(dfm_ctx* ctx, const LinearArgs& a, cudaStream_t s);
+int launch_linear_tc(dfm_ctx* ctx, const LinearArgs& a, cudaStream_t s);
+
+struct EdgeArgs {
+  int B, N, R, K;
+  int layer;
+  bool last;            // coordinate update for ligand rows
+  const int32_t* nbr;
+  const uint32_t* feat;
+  const float* radial;
+  const float* A;       // [B,N,256] W1s h_i + b1eff
+  const void* Bm;       // [B,N,256] W1d h_j  (fp32 simt / fp16 tc)
+  const float* pos;     // [B,N,3,3] (for the coordinate update)
+  float* agg;           // [B,N,256]
+  __half* mstar;        // tc path, last layer
+  float* fbuf;          // [B,L,4] out (last layer)
+};
+int launch_edge_simt(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
+int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
+int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
+
+int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s);
+int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
+                 uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s);
+int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s);
+int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s);
+int launch_force_head(dfm_ctx* ctx, int B, const float* t, Workspace& ws, float* tr_score, float* rot_score,
+                      float* f_out, cudaStream_t s);
+int launch_energy(dfm_ctx* ctx, int B, bool fp32_path, Workspace& ws, float* energy, int32_t* clashes,
+                  cudaStream_t s);
+int launch_image_pack(dfm_ctx* ctx, const float* W, int ldw, int col0, float scale, __half* img, cudaStream_t s);
+int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s);
+int launch_single_embed(dfm_ctx* ctx, const float* rec_x, const float* lig_x, cudaStream_t s);
+
+// ---- small device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: independent of launch geometry and sharding.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// kinds of draws (third counter word, high byte)
+#define RNG_EDGE 0u
+#define RNG_STEP 1u
+#define RNG_INIT 2u
+__device__ __forceinline__ uint4 dfm_rng(uint64_t seed, uint64_t stream, uint32_t kind, uint32_t index,
+                                         uint32_t a, uint32_t b) {
+  uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)(stream >> 32), (uint32_t)(seed >> 32) ^ 0x5bd1e995u);
+  uint4 ctr = make_uint4(a, b, (kind << 24) | (index & 0xffffffu), (uint32_t)stream);
+  return philox4x32(ctr, key);
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  float r = sqrtf(-2.f * logf(u01_open(a)));
+  float th = 6.283185307179586f * u01_open(b);
+  return make_float2(r * cosf(th), r * sinf(th));
+}

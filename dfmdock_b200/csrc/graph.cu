@@ -1,0 +1,281 @@
+// Pose preparation, stochastic residue graph (kNN-20 + 40 samples ~ 1/d^3) and 6D pair-feature bins.
+//
+// Reference behaviour restated here (never its code):
+//   centring                    src/models/score_net_mlsb.py:352-355
+//   get_knn_and_sample          src/models/score_net_mlsb.py:85-133   (torch.multinomial w/o replacement
+//                               == top-k of p / Exp(1): the exponential race)
+//   get_coords6d / get_bins     src/utils/coords6d.py:62-103, src/models/score_net_mlsb.py:30-70
+//   relpos                      src/inference_base.py:246-292
+// Unlike the reference, the N x N x 100 one-hot tensor is never built: only the 60 selected pairs of each
+// residue get their five bin indices, packed into one uint32.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+__constant__ float c_edge_d[39];
+__constant__ float c_edge_a[23];
+__constant__ float c_edge_p[11];
+
+static void fill_linspace(float* out, float lo, float hi, int steps) {
+  // torch.linspace (CPU, fp32): fused multiply-add from both ends.
+  float step = (hi - lo) / (float)(steps - 1);
+  for (int i = 0; i < steps; ++i)
+    out[i] = (i < steps / 2) ? fmaf(step, (float)i, lo) : fmaf(-step, (float)(steps - 1 - i), hi);
+}
+
+int dfm_upload_bin_edges() {
+  float d[39], a[23], p[11];
+  fill_linspace(d, 3.25f, 50.75f, 39);
+  fill_linspace(a, -180.f, 180.f, 23);
+  fill_linspace(p, 0.f, 180.f, 11);
+  if (cudaMemcpyToSymbol(c_edge_d, d, sizeof(d)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c_edge_a, a, sizeof(a)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c_edge_p, p, sizeof(p)) != cudaSuccess) return -1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_prepare: per trajectory, centre everything on the ligand CA centroid and build the virtual CB.
+__global__ void __launch_bounds__(256) k_prepare(int N, int R, const float* __restrict__ rec_pos,
+                                                 const float* __restrict__ lig_pos, float* __restrict__ centre,
+                                                 float* __restrict__ pos, float* __restrict__ cb) {
+  const int b = blockIdx.x, L = N - R, tid = threadIdx.x;
+  const float* lp = lig_pos + (size_t)b * L * 9;
+  __shared__ float red[3][256];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int l = tid; l < L; l += 256) {
+    sx += lp[l * 9 + 3];
+    sy += lp[l * 9 + 4];
+    sz += lp[l * 9 + 5];
+  }
+  red[0][tid] = sx; red[1][tid] = sy; red[2][tid] = sz;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      red[0][tid] += red[0][tid + o];
+      red[1][tid] += red[1][tid + o];
+      red[2][tid] += red[2][tid + o];
+    }
+    __syncthreads();
+  }
+  const float cx = red[0][0] / (float)L, cy = red[1][0] / (float)L, cz = red[2][0] / (float)L;
+  if (tid == 0) {
+    centre[b * 4 + 0] = cx; centre[b * 4 + 1] = cy; centre[b * 4 + 2] = cz; centre[b * 4 + 3] = 0.f;
+  }
+  for (int n = tid; n < N; n += 256) {
+    const float* src = (n < R) ? rec_pos + (size_t)n * 9 : lp + (size_t)(n - R) * 9;
+    float v[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) v[q] = src[q] - ((q % 3 == 0) ? cx : (q % 3 == 1) ? cy : cz);
+    float* dst = pos + ((size_t)b * N + n) * 9;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) dst[q] = v[q];
+    // virtual CB (coords6d.py:72-76)
+    float bx = v[3] - v[0], by = v[4] - v[1], bz = v[5] - v[2];
+    float cx2 = v[6] - v[3], cy2 = v[7] - v[4], cz2 = v[8] - v[5];
+    float ax = by * cz2 - bz * cy2, ay = bz * cx2 - bx * cz2, az = bx * cy2 - by * cx2;
+    float* cbo = cb + ((size_t)b * N + n) * 4;
+    cbo[0] = -0.58273431f * ax + 0.56802827f * bx - 0.54067466f * cx2 + v[3];
+    cbo[1] = -0.58273431f * ay + 0.56802827f * by - 0.54067466f * cy2 + v[4];
+    cbo[2] = -0.58273431f * az + 0.56802827f * bz - 0.54067466f * cz2 + v[5];
+    cbo[3] = 0.f;
+  }
+}
+
+int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s) {
+  k_prepare<<<B, 256, 0, s>>>(ctx->N, ctx->R, ctx->rec_pos, lig_pos, ws.centre, ws.pos, ws.cb);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float norm3(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ V3 unit3(V3 a) { float n = norm3(a); return {a.x / n, a.y / n, a.z / n}; }
+
+__device__ __forceinline__ float dihedral_deg(V3 p0, V3 p1, V3 p2, V3 p3) {
+  V3 b1 = sub3(p0, p1), b2 = sub3(p1, p2), b3 = sub3(p2, p3);
+  V3 n1 = unit3(cross3(b1, b2));
+  V3 n2 = unit3(cross3(b2, b3));
+  V3 m1 = cross3(n1, unit3(b2));
+  float ang = atan2f(dot3(m1, n2), dot3(n1, n2));
+  return ang * 180.f / 3.14159265358979323846f;
+}
+__device__ __forceinline__ float planar_deg(V3 p0, V3 p1, V3 p2) {
+  V3 v1 = sub3(p0, p1), v2 = sub3(p2, p1);
+  float ang = acosf(dot3(v1, v2) / (norm3(v1) * norm3(v2)));
+  return ang * 180.f / 3.14159265358979323846f;
+}
+template <int NE>
+__device__ __forceinline__ int count_above(const float* edges, float x) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < NE; ++k) c += (x > edges[k]) ? 1 : 0;   // NaN compares false -> bin 0
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pair_bins(const float* __restrict__ pos, const float* __restrict__ cb, int gi,
+                                              int gj, int i, int j, int R, float* radial_out) {
+  const float* pi = pos + (size_t)gi * 9;
+  const float* pj = pos + (size_t)gj * 9;
+  V3 Ni = {pi[0], pi[1], pi[2]}, CAi = {pi[3], pi[4], pi[5]};
+  V3 CAj = {pj[3], pj[4], pj[5]};
+  V3 CBi = {cb[(size_t)gi * 4], cb[(size_t)gi * 4 + 1], cb[(size_t)gi * 4 + 2]};
+  V3 CBj = {cb[(size_t)gj * 4], cb[(size_t)gj * 4 + 1], cb[(size_t)gj * 4 + 2]};
+  V3 d = sub3(CAi, CAj);
+  float r2 = d.x * d.x + d.y * d.y + d.z * d.z;
+  *radial_out = r2;
+  float dist = sqrtf(r2);
+  uint32_t db = count_above<39>(c_edge_d, dist);
+  uint32_t ob = 0, tb = 0, pb = 0;
+  if (dist < 22.0f && i != j) {
+    ob = count_above<23>(c_edge_a, dihedral_deg(CAi, CBi, CBj, CAj));
+    tb = count_above<23>(c_edge_a, dihedral_deg(Ni, CAi, CBi, CBj));
+    pb = count_above<11>(c_edge_p, planar_deg(CAi, CBi, CBj));
+  }
+  uint32_t rp;
+  if ((i < R) == (j < R)) {
+    int o = i - j + 32;
+    rp = (uint32_t)min(max(o, 0), 64);
+  } else {
+    rp = 65u;
+  }
+  return db | (ob << 6) | (tb << 11) | (pb << 16) | (rp << 20);
+}
+
+// warp-wide argmin over (value, index); ties -> smaller index
+__device__ __forceinline__ void warp_argmin(float& v, int& j) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oj = __shfl_xor_sync(0xffffffffu, j, o);
+    if (ov < v || (ov == v && oj < j)) { v = ov; j = oj; }
+  }
+}
+
+// One warp per (trajectory, residue) row.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ pos, const float* __restrict__ cb,
+        const int32_t* __restrict__ edges_in, const float* __restrict__ exp_noise, uint64_t seed,
+        uint64_t stream_base, uint32_t fwd, int32_t* __restrict__ nbr, uint32_t* __restrict__ feat,
+        float* __restrict__ radial) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npad = (N + 31) & ~31;
+  float* key = smem + (size_t)warp * (npad + 32);
+  int* knn_list = reinterpret_cast<int*>(key + npad);   // the kNN indices, for the compacted noise index
+  const long row = (long)blockIdx.x * WARPS + warp;
+  if (row >= (long)B * N) return;
+  const int b = (int)(row / N), i = (int)(row % N);
+  const size_t gbase = (size_t)b * N;
+  int sel0 = i, sel1 = i;   // neighbour for slot lane / lane+32
+
+  if (edges_in != nullptr) {
+    const int32_t* e = edges_in + (gbase + i) * K;
+    if (lane < K) sel0 = e[lane];
+    if (lane + 32 < K) sel1 = e[lane + 32];
+  } else {
+    const float* pi = pos + (gbase + i) * 9;
+    const float xi = pi[3], yi = pi[4], zi = pi[5];
+    for (int j = lane; j < N; j += 32) {
+      const float* pj = pos + (gbase + j) * 9;
+      float dx = xi - pj[3], dy = yi - pj[4], dz = zi - pj[5];
+      key[j] = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    __syncwarp();
+    // ---- kNN: knn smallest distances (the residue itself first, d = 0)
+    for (int k = 0; k < knn; ++k) {
+      float bv = FLT_MAX;
+      int bj = 0x7fffffff;
+      for (int j = lane; j < N; j += 32) {
+        float v = key[j];
+        if (v < bv) { bv = v; bj = j; }
+      }
+      warp_argmin(bv, bj);
+      if (lane == (k & 31)) { if (k < 32) sel0 = bj; else sel1 = bj; }
+      if (lane == 0) { key[bj] = FLT_MAX; knn_list[k] = bj; }
+      __syncwarp();
+    }
+    // ---- exponential race over the remaining residues: key = Exp(1) * d^3, keep the ns smallest
+    if (ns > 0) {
+      const uint64_t strm = stream_base + (uint64_t)b;
+      for (int j = lane; j < N; j += 32) {
+        float d = key[j];
+        if (d != FLT_MAX) {
+          float e;
+          if (exp_noise != nullptr) {
+            int below = 0;
+            for (int k = 0; k < knn; ++k) below += (knn_list[k] < j) ? 1 : 0;
+            e = exp_noise[(gbase + i) * (size_t)(N - knn) + (j - below)];
+          } else {
+            uint4 r4 = dfm_rng(seed, strm, RNG_EDGE, fwd, (uint32_t)(j >> 2), (uint32_t)i);
+            uint32_t u = (j & 3) == 0 ? r4.x : (j & 3) == 1 ? r4.y : (j & 3) == 2 ? r4.z : r4.w;
+            e = -logf(u01_open(u));
+          }
+          d = fmaxf(d, 1e-10f);
+          key[j] = e * (d * d * d);
+        }
+      }
+      __syncwarp();
+      for (int k = knn; k < knn + ns; ++k) {
+        float bv = FLT_MAX;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < N; j += 32) {
+          float v = key[j];
+          if (v < bv) { bv = v; bj = j; }
+        }
+        warp_argmin(bv, bj);
+        if (lane == (k & 31)) { if (k < 32) sel0 = bj; else sel1 = bj; }
+        if (lane == 0 && bj < N) key[bj] = FLT_MAX;
+        __syncwarp();
+      }
+    }
+  }
+  // ---- pair features for the K selected edges; pad slots point at the residue itself
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int k = lane + 32 * half;
+    int j = half == 0 ? sel0 : sel1;
+    uint32_t ft = 0;
+    float r2 = 0.f;
+    if (k < K) {
+      j = min(max(j, 0), N - 1);
+      ft = pair_bins(pos, cb, (int)(gbase + i), (int)(gbase + j), i, j, R, &r2);
+    } else {
+      j = i;
+    }
+    const size_t o = (gbase + i) * SLOTS + k;
+    nbr[o] = j;
+    feat[o] = ft;
+    radial[o] = r2;
+  }
+}
+
+int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
+                 uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
+  constexpr int WARPS = 8;
+  const int N = ctx->N;
+  const int npad = (N + 31) & ~31;
+  const size_t smem = (size_t)WARPS * (npad + 32) * sizeof(float);
+  if (smem > 200 * 1024) {
+    dfm_set_error("complex too large for the graph kernel (N=%d)", N);
+    return DFM_EINVAL;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_graph<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const long rows = (long)B * N;
+  const int grid = (int)((rows + WARPS - 1) / WARPS);
+  k_graph<WARPS><<<grid, WARPS * 32, smem, s>>>(B, N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, edges,
+                                                exp_noise, seed, stream_base, fwd_index, ws.nbr, ws.feat,
+                                                ws.radial);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}

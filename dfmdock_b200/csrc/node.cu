@@ -1,0 +1,285 @@
+// Per-node / per-trajectory small kernels: weight repacking, GraphNorm, force-and-torque head, energy head.
+//
+// Restates: GraphNorm (torch_geometric 2.6.0, call site src/models/egnn.py:74)
+//           heads of Score_Net.forward            src/models/score_net_mlsb.py:382-411
+//           GaussianFourierProjection             src/models/score_net_mlsb.py:162-172
+#include "common.cuh"
+
+// ---- weight repacking ----------------------------------------------------------------------------
+// fp16 image of W[256, 256] (rows = output features, K contiguous) in the tcgen05 K-major SWIZZLE_128B
+// shared-memory layout: 4 K-blocks of [256 rows x 128 B]; 16-byte chunk c of row n sits at chunk c ^ (n & 7).
+__global__ void k_image_pack(const float* __restrict__ W, int ldw, int col0, float scale, __half* __restrict__ img) {
+  const int n = blockIdx.x, k = threadIdx.x;
+  const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+  img[(((size_t)kb * 256 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(W[(size_t)n * ldw + col0 + k] * scale);
+}
+int launch_image_pack(dfm_ctx* ctx, const float* W, int ldw, int col0, float scale, __half* img, cudaStream_t s) {
+  k_image_pack<<<256, 256, 0, s>>>(W, ldw, col0, scale, img);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// T_l[r][c] = sum_e W1e[c][e] * [Ws | Wp][e][r]   (SURVEY App. A.5), plus the radial column w1r.
+__global__ void k_pair_table(const float* __restrict__ W1, const float* __restrict__ Ws, const float* __restrict__ Wp,
+                             int P, float* __restrict__ T32, __half* __restrict__ T16, float* __restrict__ w1r) {
+  const int r = blockIdx.x, c = threadIdx.x;
+  float acc = 0.f;
+  for (int e = 0; e < ED; ++e) {
+    const float emb = (r < NSPATIAL) ? Ws[e * NSPATIAL + r] : Wp[e * P + (r - NSPATIAL)];
+    acc = fmaf(W1[(size_t)c * 641 + 513 + e], emb, acc);
+  }
+  T32[(size_t)r * H + c] = acc;
+  T16[(size_t)r * H + c] = __float2half_rn(acc);
+  if (r == 0) w1r[c] = W1[(size_t)c * 641 + 512];
+}
+int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s) {
+  LayerW& w = ctx->layer[l];
+  k_pair_table<<<NSPATIAL + ctx->P, 256, 0, s>>>(w.W1, ctx->w["spatial_embed.weight"].d,
+                                                ctx->w["positional_embed.weight"].d, ctx->P, w.T32, w.T16, w.w1r);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// h0 = single_embed([rec_x; lig_x])  (score_net_mlsb.py:365-366), once per complex.
+__global__ void __launch_bounds__(256) k_single_embed(int R, int x_dim, const float* __restrict__ rec_x,
+                                                     const float* __restrict__ lig_x, const float* __restrict__ W,
+                                                     float* __restrict__ h0) {
+  const int n = blockIdx.x, c = threadIdx.x;
+  const float* x = (n < R) ? rec_x + (size_t)n * x_dim : lig_x + (size_t)(n - R) * x_dim;
+  __shared__ float xs[256];
+  float acc = 0.f;
+  for (int k0 = 0; k0 < x_dim; k0 += 256) {
+    __syncthreads();
+    xs[c] = (k0 + c < x_dim) ? x[k0 + c] : 0.f;
+    __syncthreads();
+    const int kn = min(256, x_dim - k0);
+    const float* wrow = W + (size_t)c * x_dim + k0;
+    for (int k = 0; k < kn; ++k) acc = fmaf(xs[k], __ldg(wrow + k), acc);
+  }
+  h0[(size_t)n * H + c] = acc;
+}
+int launch_single_embed(dfm_ctx* ctx, const float* rec_x, const float* lig_x, cudaStream_t s) {
+  k_single_embed<<<ctx->N, 256, 0, s>>>(ctx->R, ctx->x_dim, rec_x, lig_x, ctx->w["single_embed.weight"].d, ctx->h0);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+__global__ void k_broadcast_h0(size_t per, const float4* __restrict__ h0, float4* __restrict__ h) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < per) h[(size_t)blockIdx.y * per + idx] = h0[idx];
+}
+int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s) {
+  const size_t per = (size_t)ctx->N * H / 4;
+  dim3 grid((unsigned)((per + 255) / 256), B);
+  k_broadcast_h0<<<grid, 256, 0, s>>>(per, reinterpret_cast<const float4*>(ctx->h0), reinterpret_cast<float4*>(ws.h));
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ---- GraphNorm + SiLU ------------------------------------------------------------------------------
+// y = SiLU(weight * (z - mean*mean_scale) / sqrt(mean((z - mean*mean_scale)^2) + 1e-5) + bias), statistics over the
+// N residues of one trajectory, per feature.  grid (B, 8): 32 columns per block, 8 row lanes.
+__global__ void __launch_bounds__(256) k_graphnorm_silu(int N, const float* __restrict__ z, const float* __restrict__ gw,
+                                                       const float* __restrict__ gb, const float* __restrict__ gms,
+                                                       float* __restrict__ y) {
+  const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const float* zb = z + (size_t)b * N * H;
+  float* yb = y + (size_t)b * N * H;
+  __shared__ float red[8][32];
+  float s = 0.f;
+  for (int n = ry; n < N; n += 8) s += zb[(size_t)n * H + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) mean += red[q][threadIdx.x & 31];
+  mean /= (float)N;
+  const float shift = mean * gms[c];
+  __syncthreads();
+  float v = 0.f;
+  for (int n = ry; n < N; n += 8) {
+    const float o = zb[(size_t)n * H + c] - shift;
+    v = fmaf(o, o, v);
+  }
+  red[ry][threadIdx.x & 31] = v;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) var += red[q][threadIdx.x & 31];
+  var /= (float)N;
+  const float sd = sqrtf(var + 1e-5f);
+  const float w = gw[c], bi = gb[c];
+  for (int n = ry; n < N; n += 8) {
+    const float o = zb[(size_t)n * H + c] - shift;
+    yb[(size_t)n * H + c] = silu_acc(w * o / sd + bi);
+  }
+}
+int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s) {
+  const LayerW& w = ctx->layer[layer];
+  dim3 grid(B, 8);
+  k_graphnorm_silu<<<grid, 256, 0, s>>>(ctx->N, ws.z, w.gn_w, w.gn_b, w.gn_ms, ws.y);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ---- force / torque head -----------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum128(float v, float* red) {
+  const int tid = threadIdx.x;
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+struct HeadW {
+  const float* t_W; const float* t_lin;
+  const float* W1[2]; const float* lnw[2]; const float* lnb[2]; const float* w2[2];
+};
+
+__global__ void __launch_bounds__(128) k_force_head(int N, int R, const float* __restrict__ t, const float* __restrict__ pos,
+                                                   const float* __restrict__ fbuf, HeadW hw, float* __restrict__ tr_score,
+                                                   float* __restrict__ rot_score, float* __restrict__ f_out) {
+  const int b = blockIdx.x, tid = threadIdx.x, L = N - R;
+  __shared__ float red[4];
+  __shared__ float four[128];
+  __shared__ float temb[128];
+  // tr_pred = mean f ; rot_pred = mean r x f   (score_net_mlsb.py:393-404)
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int l = tid; l < L; l += 128) {
+    const float* f = fbuf + ((size_t)b * L + l) * 4;
+    const float* r = pos + ((size_t)b * N + R + l) * 9 + 3;
+    const float fx = f[0], fy = f[1], fz = f[2];
+    a[0] += fx; a[1] += fy; a[2] += fz;
+    a[3] += r[1] * fz - r[2] * fy;
+    a[4] += r[2] * fx - r[0] * fz;
+    a[5] += r[0] * fy - r[1] * fx;
+    if (f_out) {
+      float* fo = f_out + ((size_t)b * L + l) * 3;
+      fo[0] = fx; fo[1] = fy; fo[2] = fz;
+    }
+  }
+  float pred[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) pred[q] = block_sum128(a[q], red) / (float)L;
+  // time embedding (score_net_mlsb.py:162-172, 305-309)
+  {
+    const float tt = t[b];
+    const int k = tid & 63;
+    const float proj = tt * hw.t_W[k] * 2.f * 3.14159265358979323846f;
+    four[tid] = (tid < 64) ? sinf(proj) : cosf(proj);
+  }
+  __syncthreads();
+  {
+    float acc = 0.f;
+    const float* wr = hw.t_lin + (size_t)tid * 128;
+    for (int k = 0; k < 128; ++k) acc = fmaf(wr[k], four[k], acc);
+    temb[tid] = sigmoid_acc(acc);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const float vx = pred[which * 3], vy = pred[which * 3 + 1], vz = pred[which * 3 + 2];
+    const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float* wr = hw.W1[which] + (size_t)tid * 129;
+    float yv = wr[0] * nrm;
+    for (int k = 0; k < 128; ++k) yv = fmaf(wr[1 + k], temb[k], yv);
+    const float mean = block_sum128(yv, red) / 128.f;
+    const float dv = yv - mean;
+    const float var = block_sum128(dv * dv, red) / 128.f;
+    const float ln = dv / sqrtf(var + 1e-5f) * hw.lnw[which][tid] + hw.lnb[which][tid];
+    const float pre = block_sum128(silu_acc(ln) * hw.w2[which][tid], red);
+    const float sp = pre > 20.f ? pre : log1pf(expf(pre));
+    if (tid == 0) {
+      float* o = (which == 0 ? tr_score : rot_score) + (size_t)b * 3;
+      const float sc = sp / (nrm + 1e-6f);
+      o[0] = vx * sc; o[1] = vy * sc; o[2] = vz * sc;
+    }
+  }
+}
+int launch_force_head(dfm_ctx* ctx, int B, const float* t, Workspace& ws, float* tr_score, float* rot_score,
+                      float* f_out, cudaStream_t s) {
+  HeadW hw;
+  hw.t_W = ctx->t_W; hw.t_lin = ctx->t_lin;
+  for (int q = 0; q < 2; ++q) { hw.W1[q] = ctx->sc_W1[q]; hw.lnw[q] = ctx->sc_lnw[q]; hw.lnb[q] = ctx->sc_lnb[q]; hw.w2[q] = ctx->sc_w2[q]; }
+  k_force_head<<<B, 128, 0, s>>>(ctx->N, ctx->R, t, ws.pos, ws.fbuf, hw, tr_score, rot_score, f_out);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ---- energy head ---------------------------------------------------------------------------------------
+// E_rl = we . SiLU(LN(Wer h_r + Wel h_l)), energy = sum_{D_rl < cut} E_rl / (count + 1e-6)  (score_net_mlsb.py:385-390).
+// U = h Wer^T and V = h Wel^T are [B,N,256] GEMMs done by the caller; one warp per (b, r) walks the ligand.
+__global__ void __launch_bounds__(256) k_energy_pairs(int B, int N, int R, float cut, const float* __restrict__ U,
+                                                     const float* __restrict__ V, const float* __restrict__ pos,
+                                                     const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                     const float* __restrict__ we, float* __restrict__ esum) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + warp;
+  if (row >= (long)B * R) return;
+  const int b = (int)(row / R), r = (int)(row % R), L = N - R;
+  const float* u = U + ((size_t)b * N + r) * H + lane * 8;
+  float ur[8], gw[8], gb[8], ew[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { ur[q] = u[q]; gw[q] = lnw[lane * 8 + q]; gb[q] = lnb[lane * 8 + q]; ew[q] = we[lane * 8 + q]; }
+  const float* pr = pos + ((size_t)b * N + r) * 9 + 3;
+  const float rx = pr[0], ry = pr[1], rz = pr[2];
+  float sum = 0.f, cnt = 0.f, clash = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float* pl = pos + ((size_t)b * N + R + l) * 9 + 3;
+    const float dx = rx - pl[0], dy = ry - pl[1], dz = rz - pl[2];
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (d <= 3.0f) clash += 1.f;
+    if (!(d < cut)) continue;
+    const float* v = V + ((size_t)b * N + R + l) * H + lane * 8;
+    float x[8], s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { x[q] = ur[q] + v[q]; s += x[q]; }
+    const float mean = warp_sum(s) / 256.f;
+    float vs = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { x[q] -= mean; vs = fmaf(x[q], x[q], vs); }
+    const float rstd = 1.f / sqrtf(warp_sum(vs) / 256.f + 1e-5f);
+    float e = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) e = fmaf(silu_acc(x[q] * rstd * gw[q] + gb[q]), ew[q], e);
+    sum += warp_sum(e);
+    cnt += 1.f;
+  }
+  if (lane == 0) {
+    float* o = esum + row * 4;
+    o[0] = sum; o[1] = cnt; o[2] = clash; o[3] = 0.f;
+  }
+}
+__global__ void k_energy_finish(int R, const float* __restrict__ esum, float* __restrict__ energy, int32_t* __restrict__ clashes) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  float s = 0.f, c = 0.f, k = 0.f;
+  for (int r = lane; r < R; r += 32) {
+    const float* o = esum + ((size_t)b * R + r) * 4;
+    s += o[0]; c += o[1]; k += o[2];
+  }
+  s = warp_sum(s); c = warp_sum(c); k = warp_sum(k);
+  if (lane == 0) {
+    if (energy) energy[b] = s / (c + 1e-6f);
+    if (clashes) clashes[b] = (int32_t)(k + 0.5f);
+  }
+}
+int launch_energy(dfm_ctx* ctx, int B, bool fp32_path, Workspace& ws, float* energy, int32_t* clashes, cudaStream_t s) {
+  // U -> ws.A, V -> ws.z (both free after the last layer)
+  LinearArgs la{};
+  la.A = ws.h; la.a_scale = 1.f; la.W32 = ctx->We; la.ldw = 512; la.bias = nullptr; la.add = nullptr;
+  la.out16 = nullptr; la.M = B * ctx->N;
+  la.w_col0 = 0; la.Wimg = ctx->img_WeR; la.out = ws.A;
+  int rc = fp32_path ? launch_linear_simt(ctx, la, s) : launch_linear_tc(ctx, la, s);
+  if (rc) return rc;
+  la.w_col0 = 256; la.Wimg = ctx->img_WeL; la.out = ws.z;
+  rc = fp32_path ? launch_linear_simt(ctx, la, s) : launch_linear_tc(ctx, la, s);
+  if (rc) return rc;
+  const long rows = (long)B * ctx->R;
+  k_energy_pairs<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(B, ctx->N, ctx->R, ctx->cut_off, ws.A, ws.z, ws.pos,
+                                                          ctx->e_ln_w, ctx->e_ln_b, ctx->e_w, ws.esum);
+  LAUNCH_CHECK(ctx);
+  k_energy_finish<<<B, 32, 0, s>>>(ctx->R, ws.esum, energy, clashes);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}

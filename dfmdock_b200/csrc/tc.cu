@@ -1,0 +1,475 @@
+// tcgen05 (5th-gen tensor core) kernels for the three 256x256 contractions on the hot path:
+//   EDGE   m = SiLU(W2 SiLU(u) + b2), gate, per-residue segment sum        (src/models/egnn.py:95-116, 139-148)
+//   COORD  w = clamp(wc2 . SiLU(Wc1 m* + bc1)), coordinate displacement     (src/models/egnn.py:118-137)
+//   LINEAR out = add + A W^T + bias                                         (node_mlp, edge_mlp.0 node halves, to_energy)
+//
+// One persistent CTA per SM, 256 threads.  The fp16 weight image (128 KB, K-major SWIZZLE_128B) stays resident in
+// shared memory; a 128-row activation tile (64 KB, same layout) is rebuilt per tile; accumulators are double
+// buffered in TMEM (2 x 256 columns) so the MMA of tile t overlaps the epilogue of tile t-1.  fp16 operands,
+// fp32 accumulation; operand scaling by exact powers of two keeps fp16 in range (common.cuh).
+//
+//   D[128 x 256] (TMEM, lane = row, column = feature) = S[128 x 256] (smem) * W[256 x 256]^T (smem)
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr uint32_t W_BYTES = 256 * 256 * 2;          // 131072
+constexpr uint32_t S_BYTES = TILE_M * 256 * 2;       // 65536
+constexpr uint32_t W_KBLK = 256 * 128;               // bytes per 64-wide K block of the weight image
+constexpr uint32_t S_KBLK = TILE_M * 128;
+constexpr uint32_t OFF_W = 0;
+constexpr uint32_t OFF_S = W_BYTES;
+constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 4 x 256 floats of per-column parameters
+constexpr uint32_t OFF_PART = OFF_VEC + 4 * 256 * 4; // [2][128] gate partials
+constexpr uint32_t OFF_AGG = OFF_PART + 2 * 128 * 4; // [4][256] column partial sums
+constexpr uint32_t OFF_BAR = OFF_AGG + 4 * 256 * 4;  // 2 mbarriers + tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
+
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16-byte chunk `c16` (0..31) of tile row r -> byte offset inside the S tile (K-major SWIZZLE_128B)
+__device__ __forceinline__ uint32_t s_off(int r, int c16) {
+  return (uint32_t)(c16 >> 3) * S_KBLK + (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
+  __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
+  __half2 c = __floats2half2_rn(x[4], x[5]), d = __floats2half2_rn(x[6], x[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+__device__ __forceinline__ void add_half8(float (&u)[8], uint4 h) {
+  const __half2* p = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 f = __half22float2(p[q]);
+    u[2 * q] += f.x;
+    u[2 * q + 1] += f.y;
+  }
+}
+
+// 32 lanes x 32 values -> lane l ends with sum over lanes of v[l]   (31 shuffles)
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+enum Mode { LINEAR = 0, EDGE = 1, COORD = 2 };
+
+struct Params {
+  int mode;
+  int ntiles;
+  const __half* Wimg;
+  // LINEAR
+  LinearArgs lin;
+  // EDGE / COORD
+  EdgeArgs ed;
+  const __half* T16;
+  const float* w1r;
+  const float* v0;   // EDGE: b2    COORD: bc1   LINEAR: bias (or null)
+  const float* v1;   // EDGE: wa    COORD: wc2
+  const float* ba;   // EDGE: att bias
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  float* vec0 = reinterpret_cast<float*>(smem + OFF_VEC);
+  float* vec1 = vec0 + 256;
+  float* vec2 = vec0 + 512;                                // EDGE: w1r
+  float* part = reinterpret_cast<float*>(smem + OFF_PART); // [2][128]
+  float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);  // [4][256]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+  const uint32_t bar0 = sbase + OFF_BAR, bar1 = sbase + OFF_BAR + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: weight image -> smem, parameters, barriers, TMEM
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wimg);
+    uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
+#pragma unroll 8
+    for (int i = tid; i < (int)(W_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
+    vec0[tid] = p.v0 ? p.v0[tid] : 0.f;
+    vec1[tid] = p.v1 ? p.v1[tid] : 0.f;
+    vec2[tid] = (MODE == EDGE) ? p.w1r[tid] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int q = warp & 3, ch = warp >> 2;       // epilogue: TMEM lane quarter / column half
+  const int erow = q * 32 + lane;               // tile row owned in the epilogue
+
+  const EdgeArgs& ed = p.ed;
+  const int total_nodes = (MODE == EDGE) ? ed.B * ed.N : (MODE == COORD ? ed.B * (ed.N - ed.R) : 0);
+
+  // ---------------------------------------------------------------------------------------------
+  auto build = [&](int tile) {
+    if (MODE == LINEAR) {
+      const int c16 = lane;   // this lane converts columns 8*lane .. 8*lane+7
+#pragma unroll 4
+      for (int r = warp; r < TILE_M; r += 8) {
+        const int m = tile * TILE_M + r;
+        float x[8];
+        if (m < p.lin.M) {
+          const float4* a = reinterpret_cast<const float4*>(p.lin.A + (size_t)m * H + lane * 8);
+          float4 a0 = __ldg(a), a1 = __ldg(a + 1);
+          x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] *= p.lin.a_scale;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, c16)) = pack8(x);
+      }
+    } else if (MODE == COORD) {
+      // rows are contiguous fp16 in mstar: node pair `tile`, 64 slots each
+#pragma unroll 4
+      for (int r = warp; r < TILE_M; r += 8) {
+        const int node = tile * 2 + (r >> 6);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (node < total_nodes)
+          v = __ldg(reinterpret_cast<const uint4*>(ed.mstar + ((size_t)node * SLOTS + (r & 63)) * H) + lane);
+        *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = v;
+      }
+    } else {
+      // EDGE: S = SiLU(A_i + B_j + radial*w1r + sum of 5 table rows) * 2^-4
+      float wr[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[e] = vec2[lane * 8 + e];
+      const __half* Bm = reinterpret_cast<const __half*>(ed.Bm);
+#pragma unroll
+      for (int hn = 0; hn < 2; ++hn) {
+        const int node = tile * 2 + hn;
+        const bool nvalid = node < total_nodes;
+        float ai[8];
+        if (nvalid) {
+          const float4* a = reinterpret_cast<const float4*>(ed.A + (size_t)node * H + lane * 8);
+          float4 a0 = __ldg(a), a1 = __ldg(a + 1);
+          ai[0] = a0.x; ai[1] = a0.y; ai[2] = a0.z; ai[3] = a0.w; ai[4] = a1.x; ai[5] = a1.y; ai[6] = a1.z; ai[7] = a1.w;
+        }
+        const int b = nvalid ? node / ed.N : 0;
+#pragma unroll 2
+        for (int k = warp; k < 64; k += 8) {
+          const int r = hn * 64 + k;
+          float u[8];
+          if (nvalid && k < ed.K) {
+            const size_t eo = (size_t)node * SLOTS + k;
+            const int j = __ldg(ed.nbr + eo);
+            const uint32_t ft = __ldg(ed.feat + eo);
+            const float rad = __ldg(ed.radial + eo);
+            const uint4 hb = __ldg(reinterpret_cast<const uint4*>(Bm + ((size_t)b * ed.N + j) * H) + lane);
+            const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(ft & 63u) * H) + lane);
+            const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(40u + ((ft >> 6) & 31u)) * H) + lane);
+            const uint4 t2 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(64u + ((ft >> 11) & 31u)) * H) + lane);
+            const uint4 t3 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(88u + ((ft >> 16) & 15u)) * H) + lane);
+            const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(100u + ((ft >> 20) & 127u)) * H) + lane);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = fmaf(rad, wr[e], ai[e]);
+            add_half8(u, hb); add_half8(u, t0); add_half8(u, t1); add_half8(u, t2); add_half8(u, t3); add_half8(u, t4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = silu_f(u[e]) * S_SCALE;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = 0.f;
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(u);
+        }
+      }
+    }
+  };
+
+  // ---------------------------------------------------------------------------------------------
+  auto epilogue = [&](int tile, int buf) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
+    if (MODE == LINEAR) {
+      const int m = tile * TILE_M + erow;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (m < p.lin.M) {
+          const int col0 = ch * 128 + c * 32;
+          const size_t o = (size_t)m * H + col0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] += vec0[col0 + e];
+          if (p.lin.add) {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 ad = *reinterpret_cast<const float4*>(p.lin.add + o + e4 * 4);
+              v[e4 * 4] += ad.x; v[e4 * 4 + 1] += ad.y; v[e4 * 4 + 2] += ad.z; v[e4 * 4 + 3] += ad.w;
+            }
+          }
+          if (p.lin.out) {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4)
+              *reinterpret_cast<float4*>(p.lin.out + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+          }
+          if (p.lin.out16) {
+#pragma unroll
+            for (int e8 = 0; e8 < 4; ++e8) {
+              float x8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x8[e] = v[e8 * 8 + e];
+              *reinterpret_cast<uint4*>(p.lin.out16 + o + e8 * 8) = pack8(x8);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      return;
+    }
+    const int hn = erow >> 6, k = erow & 63;
+    const int node = tile * 2 + hn;
+    const bool valid = node < total_nodes && k < ed.K;
+    float m[128];
+    float dotp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      tmem_ld32(taddr + c * 32, v);
+      const int col0 = ch * 128 + c * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float x = silu_f(v[e] + vec0[col0 + e]);
+        if (MODE == EDGE) m[c * 32 + e] = x;
+        dotp = fmaf(x, vec1[col0 + e], dotp);
+      }
+    }
+    tc_fence_before();
+    part[ch * 128 + erow] = dotp;
+    __syncthreads();
+    const float tot = part[erow] + part[128 + erow];
+    if (MODE == COORD) {
+      // coordinate displacement of ligand residue `node` (index over B*L): mean_k diffn_k * clamp(w_k, +-2)
+      float fx = 0.f, fy = 0.f, fz = 0.f;
+      if (valid && ch == 0) {
+        const int L = ed.N - ed.R;
+        const int b = node / L, i = ed.R + node % L;
+        const size_t gi = (size_t)b * ed.N + i;
+        const int j = __ldg(ed.nbr + gi * SLOTS + k);
+        const float* pi = ed.pos + gi * 9 + 3;
+        const float* pj = ed.pos + ((size_t)b * ed.N + j) * 9 + 3;
+        const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+        const float rad = dx * dx + dy * dy + dz * dz;
+        const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
+        fx = dx * sc; fy = dy * sc; fz = dz * sc;
+      }
+      fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+      if (ch == 0 && lane == 0) { aggp[q * 4] = fx; aggp[q * 4 + 1] = fy; aggp[q * 4 + 2] = fz; }
+      __syncthreads();
+      if (tid < 2) {
+        const int nd = tile * 2 + tid;
+        if (nd < total_nodes) {
+          const float inv = 1.f / (float)ed.K;
+          float* fo = ed.fbuf + (size_t)nd * 4;
+          fo[0] = (aggp[(2 * tid) * 4] + aggp[(2 * tid + 1) * 4]) * inv;
+          fo[1] = (aggp[(2 * tid) * 4 + 1] + aggp[(2 * tid + 1) * 4 + 1]) * inv;
+          fo[2] = (aggp[(2 * tid) * 4 + 2] + aggp[(2 * tid + 1) * 4 + 2]) * inv;
+          fo[3] = 0.f;
+        }
+      }
+      return;
+    }
+    // EDGE: gate, optional m* spill for the coordinate head, segment sum over the residue's rows
+    const float g = valid ? 1.f / (1.f + __expf(-(tot + p.ba[0]))) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 128; ++e) m[e] *= g;
+    if (ed.last && valid) {
+      const int b = node / ed.N, i = node % ed.N;
+      if (i >= ed.R) {
+        __half* dst = ed.mstar + (((size_t)b * (ed.N - ed.R) + (i - ed.R)) * SLOTS + k) * H + ch * 128;
+#pragma unroll
+        for (int e8 = 0; e8 < 16; ++e8) {
+          float x8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x8[e] = m[e8 * 8 + e] * S_SCALE;
+          *reinterpret_cast<uint4*>(dst + e8 * 8) = pack8(x8);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = m[c * 32 + e];
+      const float cs = lane_transpose_sum(v, lane);
+      aggp[q * 256 + ch * 128 + c * 32 + lane] = cs;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int hn2 = 0; hn2 < 2; ++hn2) {
+      const int nd = tile * 2 + hn2;
+      if (nd < total_nodes) ed.agg[(size_t)nd * H + tid] = aggp[(2 * hn2) * 256 + tid] + aggp[(2 * hn2 + 1) * 256 + tid];
+    }
+  };
+
+  // ---------------------------------------------------------------------------------------------
+  const uint64_t dW = make_desc(sbase + OFF_W);
+  const uint64_t dS = make_desc(sbase + OFF_S);
+  int it = 0, prev_tile = -1;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    build(tile);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        // K step kk: K-block kk/4 (64 elements), 32 bytes per step inside the 128-byte swizzle row
+        const uint64_t da = dS + (uint64_t)(((kk >> 2) * S_KBLK + (kk & 3) * 32) >> 4);
+        const uint64_t db = dW + (uint64_t)(((kk >> 2) * W_KBLK + (kk & 3) * 32) >> 4);
+        mma_f16(d_tmem, da, db, kk > 0 ? 1u : 0u);
+      }
+      mma_commit(buf ? bar1 : bar0);
+    }
+    if (prev_tile >= 0) {
+      const int pb = buf ^ 1;
+      mbar_wait(pb ? bar1 : bar0, (uint32_t)(((it - 1) >> 1) & 1));
+      tc_fence_after();
+      epilogue(prev_tile, pb);
+    }
+    // the S tile may only be rebuilt once the MMA that reads it has retired
+    mbar_wait(buf ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+    tc_fence_after();
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    const int pb = (it - 1) & 1;
+    epilogue(prev_tile, pb);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int MODE>
+static int launch(dfm_ctx* ctx, const Params& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(k_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+    attr = true;
+  }
+  const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
+  if (grid <= 0) return 0;
+  k_tc<MODE><<<grid, 256, SMEM_ALLOC, s>>>(p);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace tc
+
+int launch_linear_tc(dfm_ctx* ctx, const LinearArgs& a, cudaStream_t s) {
+  tc::Params p{};
+  p.mode = tc::LINEAR;
+  p.ntiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
+  p.Wimg = a.Wimg;
+  p.lin = a;
+  p.v0 = a.bias;
+  return tc::launch<tc::LINEAR>(ctx, p, s);
+}
+
+int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
+  const LayerW& w = ctx->layer[a.layer];
+  tc::Params p{};
+  p.mode = tc::EDGE;
+  p.ntiles = (a.B * a.N + 1) / 2;
+  p.Wimg = w.img_W2;
+  p.ed = a;
+  p.T16 = w.T16;
+  p.w1r = w.w1r;
+  p.v0 = w.b2;
+  p.v1 = w.wa;
+  p.ba = w.ba;
+  return tc::launch<tc::EDGE>(ctx, p, s);
+}
+
+int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
+  const LayerW& w = ctx->layer[a.layer];
+  tc::Params p{};
+  p.mode = tc::COORD;
+  p.ntiles = (a.B * (a.N - a.R) + 1) / 2;
+  p.Wimg = w.img_Wc1;
+  p.ed = a;
+  p.v0 = w.bc1;
+  p.v1 = w.wc2;
+  return tc::launch<tc::COORD>(ctx, p, s);
+}

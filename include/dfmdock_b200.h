@@ -118,10 +118,10 @@ int dfm_reverse_step(dfm_ctx* ctx, int B, float* lig_pos, float* rot_update, flo
                      uint32_t step_index, uint32_t flags, void* stream);
 
 /* Replaces: randomize_pose (inference_base.py:318-340 / inference.py:220-242) for B trajectories.
- *   lig_pos0 [L,3,3]  input ligand pose;  quat0 [B,4] / tr0 [B,3] or NULL: injected unnormalised N(0,1)
- *   quaternion draws (scipy Rotation.random) and N(0, 30^2) translation draws; NULL -> Philox.
+ *   lig_pos0 [L,3,3]  input ligand pose;  rot0 [B,3,3] / tr0 [B,3] or NULL: injected initial rotation matrices
+ *   (scipy Rotation.random().as_matrix()) and N(0, 30^2) translation draws; NULL -> Philox.
  * Out: lig_pos [B,L,3,3], rot_update [B,3], tr_update [B,3]. */
-int dfm_randomize_pose(dfm_ctx* ctx, int B, const float* lig_pos0, const float* quat0, const float* tr0,
+int dfm_randomize_pose(dfm_ctx* ctx, int B, const float* lig_pos0, const float* rot0, const float* tr0,
                        uint64_t seed, uint64_t stream_base, uint32_t flags, float* lig_pos,
                        float* rot_update, float* tr_update, void* stream);
 
@@ -137,10 +137,12 @@ int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_steps, float 
 /* Number of kernels the library launched on behalf of this context since creation (bench.py "gpu_launches"). */
 uint64_t dfm_launch_count(const dfm_ctx* ctx);
 
-/* Debug / parity taps: copy an internal fp32 buffer of the last dfm_score_forward into `out`.
- * which: 0 = node features h after the last layer [B,N,256], 1 = packed pair-feature bins [B,N,64] (as int32),
- * 2 = radial [B,N,64].  Returns the element count or a negative error. */
-int64_t dfm_debug_read(dfm_ctx* ctx, int which, void* out, size_t out_bytes, void* workspace, void* stream);
+/* Debug / parity taps: copy an internal 4-byte-element buffer of the last dfm_score_forward (same B, same
+ * workspace) into the DEVICE buffer `out`.  which: 0 = node features h after the last node update [B,N,256],
+ * 1 = packed pair-feature bins [B,N,64] (uint32: d | omega<<6 | theta<<11 | phi<<16 | relpos<<20),
+ * 2 = radial [B,N,64], 3 = neighbour table [B,N,64] int32, 4 = last agg [B,N,256], 5 = last A [B,N,256],
+ * 6 = per-residue force [B,L,4].  Returns the element count or a negative error. */
+int64_t dfm_debug_read(dfm_ctx* ctx, int B, int which, void* out, size_t out_bytes, void* workspace, void* stream);
 
 const char* dfm_last_error(void);
 const char* dfm_version(void);
