@@ -264,6 +264,15 @@ extern "C" int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const floa
   return DFM_OK;
 }
 
+extern "C" int dfm_set_receptor_pose(dfm_ctx* ctx, const float* rec_pos, void* stream) {
+  if (!ctx || !ctx->has_complex) { dfm_set_error("no complex set"); return DFM_ESTATE; }
+  if (!rec_pos) { dfm_set_error("dfm_set_receptor_pose: null rec_pos"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMemcpyAsync(ctx->rec_pos, rec_pos, sizeof(float) * (size_t)ctx->R * 9, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return DFM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 static int linear(dfm_ctx* ctx, bool fp32, const LinearArgs& a, cudaStream_t s) {
   return fp32 ? launch_linear_simt(ctx, a, s) : launch_linear_tc(ctx, a, s);

@@ -1,0 +1,96 @@
+"""Reverse-diffusion samplers.
+
+Euler_Maruyama_sampler keeps the reference signature and RNG consumption order
+(src/inference_base.py:390-468; centre_mode=1 gives the src/inference.py:213-370 variant):
+numpy normal(4) [scipy Rotation.random] -> torch normal(1,3) -> per step {Exp(1) [N,N-20], randn(1,3), randn(1,3)}
+-> final forward {Exp(1)}.  Every tensor op of the loop body runs in the CUDA library.
+
+sample_trajectories is the batched form the reference lacks: all trajectories of a complex advance in lock step
+on one GPU (Philox noise), optionally sharded over ranks with one gather at the end (dfmdock_b200.distributed).
+"""
+import torch
+
+from . import distributed as dist_utils
+
+
+def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=1, eps=1e-3, use_clash_force=False,
+                           noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0):
+    from scipy.spatial.transform import Rotation
+
+    dev = model.device
+    time_steps = torch.linspace(1.0, eps, num_steps, device=dev)
+    dt = time_steps[0] - time_steps[1]
+    ts_host = time_steps.tolist()
+    dt_host = float(dt)
+
+    rec_pos = batch["rec_pos"].clone().to(dev)
+    lig_pos0 = batch["lig_pos"].clone().to(dev)
+    model.set_complex(batch)
+
+    # randomize_pose (inference_base.py:318-340): same draws, same order
+    rot0 = torch.from_numpy(Rotation.random().as_matrix()).float()
+    tr0 = torch.normal(0.0, 30.0, size=(1, 3), device=dev)
+    lig_pos, tr_update, rot_update = model.randomize_pose(lig_pos0, 1, rot0=rot0[None], tr0=tr0, centre_mode=centre_mode)
+
+    output = None
+    with torch.no_grad():
+        for i in range(num_steps):
+            t_host = ts_host[i]
+            is_last = i == num_steps - 1
+            batch["t"] = torch.ones(batch_size, device=dev) * t_host
+            batch["rec_pos"] = rec_pos
+            batch["lig_pos"] = lig_pos[0]
+            output = model(batch)
+            if noise_annealing:
+                ns_tr = ns_rot = t_host
+            elif is_last:
+                ns_tr = ns_rot = 0.0
+            else:
+                ns_tr, ns_rot = tr_noise_scale, rot_noise_scale
+            z = torch.cat([torch.randn(1, 3, device=dev), torch.randn(1, 3, device=dev)], dim=0)   # rot, then tr
+            model.reverse_step(lig_pos, rot_update, tr_update, output["tr_score"], output["rot_score"], t_host, dt_host,
+                               ns_rot, ns_tr, z=z[None], use_clash_force=use_clash_force, centre_mode=centre_mode)
+            if is_last:
+                batch["rec_pos"] = rec_pos
+                batch["lig_pos"] = lig_pos[0]
+                output = model(batch)
+    return rec_pos, lig_pos[0], rot_update, tr_update, output
+
+
+def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_clash_force=False, noise_annealing=False,
+                        tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, seed=0, max_batch=None, group=None,
+                        gather_poses=False):
+    """All `num_samples` trajectories of one complex.  Under torch.distributed each rank runs a contiguous slice
+    (trajectory k always uses Philox subsequence k, so the result does not depend on the number of ranks) and the
+    [T,8] result table (rot_update 3, tr_update 3, energy, num_clashes) is all-gathered once.
+
+    Returns dict with global tensors: rot_update [T,3], tr_update [T,3], energy [T], num_clashes [T], best (argmin energy),
+    and lig_pos [T,L,3,3] if gather_poses (else the local slice under "lig_pos_local").
+    """
+    rank, world = dist_utils.rank_world(group)
+    lo, hi = dist_utils.shard_range(num_samples, rank, world)
+    model.set_complex(batch)
+    dev = model.device
+    L = batch["lig_pos"].shape[0]
+    chunks = []
+    step = max_batch or max(hi - lo, 1)
+    for c0 in range(lo, hi, step):
+        c1 = min(hi, c0 + step)
+        chunks.append(model.sample(batch["lig_pos"], c1 - c0, num_steps=num_steps, eps=eps, tr_noise_scale=tr_noise_scale,
+                                   rot_noise_scale=rot_noise_scale, use_clash_force=use_clash_force,
+                                   noise_annealing=noise_annealing, centre_mode=centre_mode, seed=seed, stream_base=c0))
+    if chunks:
+        local = {k: torch.cat([c[k] for c in chunks], dim=0) for k in chunks[0]}
+    else:
+        local = {"lig_pos": torch.empty(0, L, 3, 3, device=dev), "rot_update": torch.empty(0, 3, device=dev),
+                 "tr_update": torch.empty(0, 3, device=dev), "energy": torch.empty(0, device=dev),
+                 "num_clashes": torch.empty(0, dtype=torch.int32, device=dev)}
+    table = torch.cat([local["rot_update"], local["tr_update"], local["energy"][:, None],
+                       local["num_clashes"].float()[:, None]], dim=1)
+    full = dist_utils.gather_rows(table, num_samples, group)
+    out = {"rot_update": full[:, 0:3], "tr_update": full[:, 3:6], "energy": full[:, 6],
+           "num_clashes": full[:, 7].round().long(), "lig_pos_local": local["lig_pos"], "local_range": (lo, hi)}
+    if gather_poses:
+        out["lig_pos"] = dist_utils.gather_rows(local["lig_pos"].reshape(hi - lo, -1), num_samples, group).view(-1, L, 3, 3)
+    out["best"] = int(torch.argmin(out["energy"]).item()) if num_samples > 0 else -1
+    return out

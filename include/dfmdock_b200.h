@@ -82,6 +82,10 @@ int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream);
 int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const float* rec_x, const float* lig_x,
                     const float* rec_pos, float sym, void* stream);
 
+/* Replaces only the receptor backbone [R,3,3] of the current complex (the reference sampler re-sends
+ * batch["rec_pos"] every step, inference_base.py:422); R must equal the current complex's. */
+int dfm_set_receptor_pose(dfm_ctx* ctx, const float* rec_pos, void* stream);
+
 /* Bytes of scratch dfm_score_forward / dfm_sample need for B simultaneous trajectories of the current complex. */
 size_t dfm_workspace_bytes(const dfm_ctx* ctx, int B);
 
