@@ -1,0 +1,276 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Tolerances (stated per mode):
+  fp32  (DFM_PRECISION_FP32, FFMA kernels):            5e-4 relative (L2) on f / scores / h, 2e-3 absolute on energy
+  fp16  (default: fp16 tcgen05 operands, fp32 accum):  2e-2 relative (L2) on f / scores / h, 5e-2 absolute on energy
+  integer outputs (bins, num_clashes, neighbour sets with injected noise): exact, except pair-feature bins whose
+  angle lies within 1e-3 degree of a bin edge (libm vs CUDA atan2/acos): at most 0.05% of the bins may differ.
+"""
+import pytest
+import torch
+
+from util import FWD_CASES, case_small, load_golden, max_abs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(rel=5e-4, energy=2e-3), "fp16": dict(rel=2e-2, energy=5e-2)}
+
+
+def _model(sd, hp, precision):
+    from dfmdock_b200 import Score_Model
+    return Score_Model(sd, hp, precision=precision).to("cuda")
+
+
+def _unpack_bins(ft):
+    ft = ft.long()
+    return ft & 63, (ft >> 6) & 31, (ft >> 11) & 31, (ft >> 16) & 15, (ft >> 20) & 127
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", list(FWD_CASES))
+def test_forward_injected_edges_vs_reference_golden(name, precision):
+    sd, hp, batch = FWD_CASES[name]()
+    model = _model(sd, hp, precision)
+    model.set_complex(batch)
+    R, L = batch["rec_pos"].shape[0], batch["lig_pos"].shape[0]
+    N = R + L
+    tol = TOL[precision]
+    for item in load_golden(name):
+        nbr = item["nbr"].long()
+        K = nbr.shape[1]
+        out = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), edges=nbr[None].int(), want_energy=True)
+        torch.cuda.synchronize()
+        for k in ("f", "tr_score", "rot_score"):
+            e = rel_err(out[k].cpu()[0], item[k].reshape(out[k].shape[1:]))
+            assert e <= tol["rel"], (name, precision, k, e)
+        assert abs(float(out["energy"][0]) - float(item["energy"])) <= tol["energy"]
+        assert int(out["num_clashes"][0]) == int(item["num_clashes"])
+        h = model.debug_read(1, 0, (N, 256)).cpu()
+        assert rel_err(h, item["h"][5].float()) <= max(tol["rel"], 2e-3)      # golden h is stored in fp16
+        # integer pair features of the selected edges
+        ft = model.debug_read(1, 1, (N, 64), dtype=torch.int32).cpu()[:, :K]
+        d, o, t, p, rp = _unpack_bins(ft)
+        rows = torch.arange(N)[:, None].expand(N, K)
+        gb = item["bins"].long()
+        mism = sum(int((x != gb[q][rows, nbr]).sum()) for q, x in enumerate((d, o, t, p)))
+        assert mism <= max(1, int(5e-4 * 4 * N * K)), mism
+        from dfmdock_b200.features import relpos_bins
+        assert torch.equal(rp, relpos_bins(R, L)[rows, nbr])
+
+
+@pytest.mark.parametrize("name", list(FWD_CASES))
+def test_graph_with_injected_exp_noise_matches_reference(name):
+    sd, hp, batch = FWD_CASES[name]()
+    model = _model(sd, hp, "fp32")
+    model.set_complex(batch)
+    for item in load_golden(name):
+        out = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), exp_noise=item["exp"][None], return_edges=True)
+        got = out["edges"][0].cpu().long()
+        want = item["nbr"].long()
+        nk = min(20, want.shape[1])
+        # kNN block: identical order (ascending distance); sampled block: same set (order = key order, also identical)
+        bad_rows = int((got.sort(dim=1).values != want.sort(dim=1).values).any(dim=1).sum())
+        assert bad_rows <= max(1, want.shape[0] // 50), bad_rows      # near-tie flips only (cdist mm-path rounding)
+        assert int((got[:, :nk] != want[:, :nk]).any(dim=1).sum()) <= max(1, want.shape[0] // 50)
+
+
+def test_philox_graph_properties():
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp32")
+    model.set_complex(batch)
+    lig = batch["lig_pos"][None].repeat(3, 1, 1, 1)
+    t = torch.full((3,), 0.5)
+    a = model.score(lig, t, seed=5, stream_base=10, forward_index=2, return_edges=True)["edges"].cpu().long()
+    b = model.score(lig, t, seed=5, stream_base=10, forward_index=2, return_edges=True)["edges"].cpu().long()
+    c = model.score(lig, t, seed=5, stream_base=10, forward_index=3, return_edges=True)["edges"].cpu().long()
+    d = model.score(lig[1:], t[1:], seed=5, stream_base=11, forward_index=2, return_edges=True)["edges"].cpu().long()
+    assert torch.equal(a, b)                       # deterministic
+    assert not torch.equal(a, c)                   # new draws every forward
+    assert torch.equal(a[1:], d)                   # trajectory k's stream does not depend on batch composition / sharding
+    assert not torch.equal(a[0, :, 20:], a[1, :, 20:])
+    N = a.shape[1]
+    pos = torch.cat([batch["rec_pos"], batch["lig_pos"]], 0)[:, 1]
+    dm = torch.cdist(pos.double(), pos.double())
+    knn = torch.topk(dm, 20, largest=False).indices
+    assert torch.equal(a[0, :, :20].sort(1).values, knn.sort(1).values)
+    for r in range(N):
+        row = a[0, r].tolist()
+        assert len(set(row)) == 60 and min(row) >= 0 and max(row) < N
+    # sampled neighbours prefer close residues (p ~ d^-3): mean sampled distance well below the mean over non-kNN residues
+    samp_d = dm.gather(1, a[0, :, 20:]).mean()
+    mask = torch.ones_like(dm, dtype=torch.bool).scatter_(1, knn, False)
+    assert float(samp_d) < float(dm[mask].mean())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_batched_equals_single(precision):
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, precision)
+    model.set_complex(batch)
+    item = load_golden("fwd_synth_n70.pt")[0]
+    g = torch.Generator().manual_seed(0)
+    ligs = torch.stack([batch["lig_pos"] + torch.randn(1, 1, 3, generator=g) * 3 for _ in range(5)], 0)
+    edges = item["nbr"][None].int().repeat(5, 1, 1)
+    t = torch.tensor([0.9, 0.7, 0.5, 0.3, 0.1])
+    full = model.score(ligs, t, edges=edges, want_energy=True)
+    full = {k: v.clone() for k, v in full.items()}
+    for i in range(5):
+        one = model.score(ligs[i:i + 1], t[i:i + 1], edges=edges[i:i + 1], want_energy=True)
+        for k in ("f", "tr_score", "rot_score", "energy"):
+            assert torch.equal(one[k][0], full[k][i]), (k, i)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_rotation_equivariance_full_size(precision):
+    """Size-independent property at the benchmark size (2 x 150): with the graph held fixed, rotating + translating the
+    whole complex rotates forces and scores and leaves the energy unchanged."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    from oracle.dfmdock_oracle import aa_to_mat
+    batch = synthetic_complex(150, 150, seed=0)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([12.0, 0.0, 0.0])
+    model = _model(synthetic_state_dict(0, 66), synthetic_hparams(66), precision)
+    model.set_complex(batch)
+    t = torch.tensor([0.4])
+    o1 = model.score(batch["lig_pos"][None], t, seed=1, return_edges=True, want_energy=True)
+    o1 = {k: v.clone() for k, v in o1.items()}
+    Rm = aa_to_mat(torch.tensor([[0.3, -1.1, 0.7]]))[0]
+    shift = torch.tensor([5.0, -3.0, 11.0])
+    b2 = dict(batch)
+    b2["rec_pos"] = batch["rec_pos"] @ Rm.T + shift
+    b2["lig_pos"] = batch["lig_pos"] @ Rm.T + shift
+    model.set_complex(b2)
+    o2 = model.score(b2["lig_pos"][None], t, edges=o1["edges"], want_energy=True)
+    tol = 2e-3 if precision == "fp32" else 3e-2
+    Rg = Rm.cuda()
+    assert rel_err(o2["f"][0].cpu(), (o1["f"][0] @ Rg.T).cpu()) <= tol
+    assert rel_err(o2["tr_score"].cpu(), (o1["tr_score"] @ Rg.T).cpu()) <= tol
+    assert rel_err(o2["rot_score"].cpu(), (o1["rot_score"] @ Rg.T).cpu()) <= tol
+    assert abs(float(o2["energy"][0]) - float(o1["energy"][0])) <= (5e-3 if precision == "fp32" else 5e-2)
+    assert int(o2["num_clashes"][0]) == int(o1["num_clashes"][0])
+
+
+def test_fp16_tensor_core_path_tracks_fp32_path():
+    sd, hp, batch = case_small()
+    item = load_golden("fwd_synth_n70.pt")[0]
+    outs = {}
+    for precision in ("fp32", "fp16"):
+        model = _model(sd, hp, precision)
+        model.set_complex(batch)
+        o = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), edges=item["nbr"][None].int(), want_energy=True)
+        outs[precision] = {k: v.cpu().clone() for k, v in o.items()}
+    for k in ("f", "tr_score", "rot_score"):
+        assert rel_err(outs["fp16"][k], outs["fp32"][k]) <= 2e-2, k
+
+
+@pytest.mark.parametrize("name,centre_mode", [("sampler_base_n70.pt", 0), ("sampler_near_n70.pt", 0), ("sampler_clash_n70.pt", 1)])
+def test_reverse_steps_teacher_forced_vs_reference_golden(name, centre_mode):
+    """T3: one reverse step at a time from the reference's own poses, scores and noise."""
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp32")
+    model.set_complex(batch)
+    g = load_golden(name)
+    S = g["num_steps"]
+    ts = torch.linspace(1.0, 1e-3, S)
+    dt = float(ts[0] - ts[1])
+    lig, tr_u, rot_u = model.randomize_pose(batch["lig_pos"], 1, rot0=g["rot0"][None], tr0=g["tr0"], centre_mode=centre_mode)
+    assert max_abs(lig[0].cpu(), g["fwd_lig_pos"][0]) <= 2e-4
+    for i in range(S):
+        last = i == S - 1
+        lig = g["fwd_lig_pos"][i][None].cuda().contiguous()
+        ns = 0.0 if last else 0.5
+        model.reverse_step(lig, rot_u, tr_u, g["tr_score"][i].cuda(), g["rot_score"][i].cuda(), float(ts[i]), dt, ns, ns,
+                           z=g["z"][i][None], use_clash_force=g["use_clash_force"], centre_mode=centre_mode)
+        want = g["fwd_lig_pos"][i + 1]
+        assert max_abs(lig[0].cpu(), want) <= 3e-5 * float(want.abs().max()) + 2e-4, (i, max_abs(lig[0].cpu(), want))
+    assert max_abs(tr_u.cpu(), g["tr_update"]) <= 3e-5 * float(g["tr_update"].abs().max()) + 2e-4
+    from oracle.dfmdock_oracle import aa_to_mat
+    assert max_abs(aa_to_mat(rot_u.cpu()), aa_to_mat(g["rot_update"])) <= 2e-5
+
+
+def test_clash_force_vs_reference_golden():
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp32")
+    model.set_complex(batch)
+    zero = torch.zeros(1, 3, device="cuda")
+    for item in load_golden("clash_force_n70.pt"):
+        lig = item["lig_pos"][None].cuda().contiguous()
+        rot_u, tr_u = torch.zeros(1, 3, device="cuda"), torch.zeros(1, 3, device="cuda")
+        model.reverse_step(lig, rot_u, tr_u, zero, zero, 0.5, 0.01, 0.0, 0.0, z=torch.zeros(1, 2, 3), use_clash_force=True)
+        moved = (lig[0].cpu() - item["lig_pos"]).reshape(-1, 3)
+        assert max_abs(moved.mean(0), item["force"]) <= 1e-4 * max(1.0, float(item["force"].abs().max()))
+        assert max_abs(tr_u[0].cpu(), item["force"]) <= 1e-4 * max(1.0, float(item["force"].abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_score_along_reference_trajectory(precision):
+    """T4 (teacher forced): scores at every pose the reference visited, same Exp(1) draws."""
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, precision)
+    model.set_complex(batch)
+    g = load_golden("sampler_near_n70.pt")
+    S = g["num_steps"]
+    ts = torch.linspace(1.0, 1e-3, S)
+    tol = TOL[precision]["rel"]
+    for i in range(S + 1):
+        t = ts[min(i, S - 1)]
+        o = model.score(g["fwd_lig_pos"][i][None], t[None], edges=g["nbr"][i][None].int(), want_energy=(i == S))
+        assert rel_err(o["tr_score"].cpu(), g["tr_score"][i]) <= tol, i
+        assert rel_err(o["rot_score"].cpu(), g["rot_score"][i]) <= tol, i
+    assert abs(float(o["energy"][0]) - float(g["energy"])) <= TOL[precision]["energy"]
+    assert int(o["num_clashes"][0]) == int(g["num_clashes"])
+
+
+def test_sample_api_sharding_invariance_and_determinism():
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp16")
+    model.set_complex(batch)
+    a = model.sample(batch["lig_pos"], 4, num_steps=4, seed=9, stream_base=0)
+    a = {k: v.clone() for k, v in a.items()}
+    b = model.sample(batch["lig_pos"], 4, num_steps=4, seed=9, stream_base=0)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.isfinite(a[k].float()).all(), k
+    lo = model.sample(batch["lig_pos"], 2, num_steps=4, seed=9, stream_base=0)
+    lo = {k: v.clone() for k, v in lo.items()}
+    hi = model.sample(batch["lig_pos"], 2, num_steps=4, seed=9, stream_base=2)
+    for k in a:
+        assert torch.equal(torch.cat([lo[k], hi[k]], 0), a[k]), k
+    c = model.sample(batch["lig_pos"], 4, num_steps=4, seed=10, stream_base=0)
+    assert not torch.equal(c["rot_update"], a["rot_update"])
+    # the accumulated rigid transform reproduces the final pose: x_final = R_tot (x0 - c0) + c0 + tr_tot
+    from oracle.dfmdock_oracle import aa_to_mat
+    x0 = batch["lig_pos"]
+    c0 = x0[:, 1].mean(0)
+    for k in range(4):
+        Rt = aa_to_mat(a["rot_update"][k:k + 1].cpu())[0]
+        want = (x0 - c0) @ Rt.T + c0 + a["tr_update"][k].cpu()
+        assert max_abs(a["lig_pos"][k].cpu(), want) <= 2e-3 * max(1.0, float(want.abs().max()))
+
+
+def test_reference_signature_sampler_runs():
+    from dfmdock_b200 import Euler_Maruyama_sampler
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp16")
+    torch.manual_seed(0)
+    import numpy as np
+    np.random.seed(0)
+    b = {k: v.cuda() for k, v in batch.items()}
+    rec_pos, lig_pos, rot_update, tr_update, out = Euler_Maruyama_sampler(model, b, num_steps=3, device="cuda", use_clash_force=True)
+    assert lig_pos.shape == batch["lig_pos"].shape and rot_update.shape == (1, 3) and tr_update.shape == (1, 3)
+    assert set(out) >= {"tr_score", "rot_score", "energy", "f", "num_clashes"}
+    assert torch.isfinite(lig_pos).all() and torch.isfinite(out["energy"])
+
+
+def test_errors_are_loud():
+    from dfmdock_b200 import Score_Model
+    sd, hp, batch = case_small()
+    with pytest.raises(RuntimeError):
+        Score_Model(sd, hp).to("cpu")
+    bad = dict(sd)
+    del bad["network.EGNN_3.egcl.edge_mlp.2.weight"]
+    with pytest.raises(RuntimeError, match="missing weight"):
+        Score_Model(bad, hp).to("cuda")
+    m = _model(sd, hp, "fp16")
+    with pytest.raises((RuntimeError, TypeError)):
+        m.score(batch["lig_pos"][None], torch.tensor([0.5]))     # no complex set
