@@ -41,10 +41,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();   // a lost MMA completion must fail loudly, never hang the GPU
   } while (!ok);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -68,10 +68,13 @@ def test_graph_with_injected_exp_noise_matches_reference(name):
         got = out["edges"][0].cpu().long()
         want = item["nbr"].long()
         nk = min(20, want.shape[1])
-        # kNN block: identical order (ascending distance); sampled block: same set (order = key order, also identical)
-        bad_rows = int((got.sort(dim=1).values != want.sort(dim=1).values).any(dim=1).sum())
-        assert bad_rows <= max(1, want.shape[0] // 50), bad_rows      # near-tie flips only (cdist mm-path rounding)
-        assert int((got[:, :nk] != want[:, :nk]).any(dim=1).sum()) <= max(1, want.shape[0] // 50)
+        # kNN block and sampled block must hold the same residues (order inside a block is irrelevant to the sum over
+        # edges, and the synthetic chains have exact distance ties: d(i,i-1) = d(i,i+1) = 3.8 A).  The reference's
+        # cdist uses the |a|^2+|b|^2-2ab path (up to 0.04 A off), so a near-tie at the kNN boundary may flip: <= 2% of rows.
+        budget = max(1, want.shape[0] // 50)
+        bad_knn = int((got[:, :nk].sort(dim=1).values != want[:, :nk].sort(dim=1).values).any(dim=1).sum())
+        bad_smp = int((got[:, nk:].sort(dim=1).values != want[:, nk:].sort(dim=1).values).any(dim=1).sum())
+        assert bad_knn <= budget and bad_smp <= budget, (bad_knn, bad_smp)
 
 
 def test_philox_graph_properties():
