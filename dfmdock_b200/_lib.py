@@ -37,6 +37,8 @@ PROTOTYPES = {
     "dfm_sample": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_float, c_uint32, c_uint64, c_uint64,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dfm_launch_count": (c_uint64, [c_void_p]),
+    "dfm_profile_enable": (c_int, [c_void_p, c_int]),
+    "dfm_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int)]),
     "dfm_debug_read": (c_int64, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dfm_last_error": (c_char_p, []),
     "dfm_version": (c_char_p, []),

@@ -98,6 +98,7 @@ extern "C" void dfm_destroy(dfm_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& kv : ctx->w) cudaFree(kv.second.d);
   for (void* p : ctx->owned) cudaFree(p);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaFree(ctx->h0);
   cudaFree(ctx->rec_pos);
   delete ctx;
@@ -310,12 +311,18 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
     ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
+    const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
+    if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
     if (fp32) {
       if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
     } else {
       if ((rc = launch_edge_tc(ctx, ea, s))) return rc;
-      if (last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
     }
+    if (prof) {
+      CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], s));
+      ctx->prof_used += 2;
+    }
+    if (!fp32 && last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
     if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
     // z = W3h h + b3 + W3a agg
     la.A = ws.h; la.a_scale = 1.f; la.W32 = w.W3; la.ldw = 512; la.w_col0 = 0; la.Wimg = w.img_W3h; la.bias = w.b3;
@@ -441,6 +448,37 @@ extern "C" int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_st
                              fflags | DFM_WANT_ENERGY, trs, rots, nullptr, energy, num_clashes, nullptr, ws, s))) return rc;
     }
   }
+  return DFM_OK;
+}
+
+extern "C" int dfm_profile_enable(dfm_ctx* ctx, int max_launches) {
+  if (!ctx) { dfm_set_error("null ctx"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  ctx->prof_events.clear();
+  ctx->prof_used = 0;
+  ctx->profile = max_launches > 0;
+  for (int i = 0; i < 2 * max_launches; ++i) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    ctx->prof_events.push_back(e);
+  }
+  return DFM_OK;
+}
+
+extern "C" int dfm_profile_read(dfm_ctx* ctx, double* edge_kernel_ms, int* launches) {
+  if (!ctx || !edge_kernel_ms || !launches) { dfm_set_error("dfm_profile_read: bad argument"); return DFM_EINVAL; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(ctx->prof_events[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    total += ms;
+  }
+  *edge_kernel_ms = total;
+  *launches = (int)(ctx->prof_used / 2);
+  ctx->prof_used = 0;
   return DFM_OK;
 }
 

@@ -112,6 +112,10 @@ struct dfm_ctx {
   size_t h0_cap = 0, rec_cap = 0;
   uint64_t launches = 0;
   int num_sms = 148;
+  // optional CUDA-event timing of the dominant (edge) kernel, for bench.py's roofline line
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+  size_t prof_used = 0;
   std::vector<void*> owned;   // cudaMalloc'd derived buffers
 };
 

@@ -275,6 +275,15 @@ class Score_Model:
                 _lib.ptr(out["energy"]), _lib.ptr(out["num_clashes"]), ws, nws, self._stream()), "dfm_sample")
         return out
 
+    def profile_enable(self, max_launches):
+        _lib.check(_lib.load().dfm_profile_enable(self._ctx, int(max_launches)), "dfm_profile_enable")
+
+    def profile_read(self):
+        """-> (summed edge-kernel milliseconds, launches) since the last read; synchronises on the recorded events."""
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        _lib.check(_lib.load().dfm_profile_read(self._ctx, ctypes.byref(ms), ctypes.byref(n)), "dfm_profile_read")
+        return ms.value, n.value
+
     @property
     def launch_count(self):
         return int(_lib.load().dfm_launch_count(self._ctx)) if self._ctx is not None else 0

@@ -141,6 +141,12 @@ int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_steps, float 
 /* Number of kernels the library launched on behalf of this context since creation (bench.py "gpu_launches"). */
 uint64_t dfm_launch_count(const dfm_ctx* ctx);
 
+/* Measurement hooks (bench.py "roofline"): when enabled, every launch of the dominant kernel (the fused edge
+ * kernel) is bracketed by CUDA events on the caller's stream.  dfm_profile_read synchronises on those events and
+ * returns the summed kernel time and the number of launches since the last read. */
+int dfm_profile_enable(dfm_ctx* ctx, int max_launches);
+int dfm_profile_read(dfm_ctx* ctx, double* edge_kernel_ms, int* launches);
+
 /* Debug / parity taps: copy an internal 4-byte-element buffer of the last dfm_score_forward (same B, same
  * workspace) into the DEVICE buffer `out`.  which: 0 = node features h after the last node update [B,N,256],
  * 1 = packed pair-feature bins [B,N,64] (uint32: d | omega<<6 | theta<<11 | phi<<16 | relpos<<20),

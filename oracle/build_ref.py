@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY.  Extracts what the real-checkpoint parity tests need from the mounted reference tree into
+the git-ignored oracle/_ref/ (which travels to the GPU box with the repo snapshot):
+    oracle/_ref/pinder_0.pt, dips_model_0.pt   {"state_dict", "hparams"} of weights/pinder_0.ckpt, checkpoints/dips/model_0.ckpt
+    oracle/_ref/db5_<id>.pt                     {"receptor": {x,pos,seq}, "ligand": {...}} of data/db5_test/<id>.pt
+    oracle/_ref/golden_real.pt                  reference outputs on those inputs (live reference, injected edges)
+No reference SOURCE is copied -- only data files re-serialised without the omegaconf / torch_geometric pickles.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "oracle", "_ref")
+COMPLEXES = ["1QA9", "7CEI", "4POU"]
+
+
+def main(quiet=False, force=False):
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        if not quiet:
+            print("reference tree not mounted; nothing to do")
+        return
+    os.makedirs(OUT, exist_ok=True)
+    done = os.path.join(OUT, "golden_real.pt")
+    if os.path.exists(done) and not force:
+        return
+    from dfmdock_b200.checkpoint import load_checkpoint, load_db5_record
+    from dfmdock_b200.features import batch_from_record
+    root = ref_shims.REFERENCE_ROOT
+    ck = {"pinder_0": os.path.join(root, "weights", "pinder_0.ckpt"), "dips_model_0": os.path.join(root, "checkpoints", "dips", "model_0.ckpt")}
+    for name, path in ck.items():
+        sd, hp = load_checkpoint(path)
+        torch.save({"state_dict": sd, "hparams": hp}, os.path.join(OUT, name + ".pt"))
+    recs = {}
+    for cid in COMPLEXES:
+        recs[cid] = load_db5_record(os.path.join(root, "data", "db5_test", cid + ".pt"))
+        torch.save(recs[cid], os.path.join(OUT, "db5_%s.pt" % cid))
+    # goldens from the live reference: real checkpoints x real complexes, graph captured and stored
+    golden = []
+    ref_shims.install()
+    import models.score_net_mlsb as snm
+    for ck_name, path in ck.items():
+        model, hp = ref_shims.build_reference_model(path)
+        width = hp.model["positional_embed_dim"]
+        for cid in COMPLEXES:
+            batch = batch_from_record(recs[cid], pos_width=width)
+            for t in (0.9, 0.1):
+                batch["t"] = torch.tensor([t])
+                captured = {}
+                orig = snm.get_knn_and_sample
+
+                def gk(points, *a, **k):
+                    out = orig(points, *a, **k)
+                    captured["nbr"] = torch.cat([o for o in out if o is not None], dim=-1).clone()
+                    return out
+
+                snm.get_knn_and_sample = gk
+                try:
+                    torch.manual_seed(hash((ck_name, cid)) % 1000)
+                    with torch.no_grad():
+                        out = model(batch)
+                finally:
+                    snm.get_knn_and_sample = orig
+                golden.append({"ckpt": ck_name, "complex": cid, "t": t, "nbr": captured["nbr"].to(torch.int16),
+                               "tr_score": out["tr_score"], "rot_score": out["rot_score"], "energy": out["energy"],
+                               "f": out["f"], "num_clashes": out["num_clashes"]})
+    torch.save(golden, done)
+    if not quiet:
+        print("wrote", OUT, [(g["ckpt"], g["complex"], g["t"], float(g["energy"])) for g in golden])
+
+
+if __name__ == "__main__":
+    main(force="--force" in sys.argv)

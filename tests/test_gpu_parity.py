@@ -277,3 +277,40 @@ def test_errors_are_loud():
     m = _model(sd, hp, "fp16")
     with pytest.raises((RuntimeError, TypeError)):
         m.score(batch["lig_pos"][None], torch.tensor([0.5]))     # no complex set
+
+
+REAL = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))), "oracle", "_ref")
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(__import__("os").path.join(REAL, "golden_real.pt")),
+                    reason="oracle/_ref not built (python oracle/build_ref.py in the build container)")
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_real_checkpoints_real_complexes_vs_live_reference_golden(precision):
+    """weights/pinder_0.ckpt and checkpoints/dips/model_0.ckpt on db5 complexes 1QA9 / 7CEI / 4POU; goldens are outputs of
+    the unmodified reference (oracle/build_ref.py), graph injected."""
+    import os
+    from dfmdock_b200 import Score_Model
+    from dfmdock_b200.features import batch_from_record
+    golden = torch.load(os.path.join(REAL, "golden_real.pt"), weights_only=False)
+    tol = TOL[precision]
+    models = {}
+    worst = {}
+    for g in golden:
+        if g["ckpt"] not in models:
+            ck = torch.load(os.path.join(REAL, g["ckpt"] + ".pt"), weights_only=False)
+            models[g["ckpt"]] = Score_Model(ck["state_dict"], ck["hparams"], precision=precision).to("cuda")
+        model = models[g["ckpt"]]
+        rec = torch.load(os.path.join(REAL, "db5_%s.pt" % g["complex"]), weights_only=False)
+        batch = batch_from_record(rec, pos_width=model.pos_width)
+        model.set_complex(batch)
+        out = model.score(batch["lig_pos"][None], torch.tensor([g["t"]]), edges=g["nbr"][None].int(), want_energy=True)
+        for k in ("f", "tr_score", "rot_score"):
+            e = rel_err(out[k].cpu()[0], g[k].reshape(out[k].shape[1:]))
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e <= tol["rel"] * (1.0 if k == "f" else 1.0), (g["ckpt"], g["complex"], g["t"], k, e)
+        de = abs(float(out["energy"][0]) - float(g["energy"]))
+        worst["energy"] = max(worst.get("energy", 0.0), de)
+        # energies are O(20-60) here: scale the absolute tolerance
+        assert de <= tol["energy"] * max(1.0, abs(float(g["energy"])) / 10.0), (g["ckpt"], g["complex"], de)
+        assert int(out["num_clashes"][0]) == int(g["num_clashes"])
+    print("worst errors", precision, worst)
