@@ -183,6 +183,8 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     const size_t trows = NSPATIAL + ctx->P;
     if ((rc = dev_alloc(ctx, &w.T32, trows * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.T16, trows * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.Tdrp16, (size_t)2 * 40 * 66 * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.Totp16, (size_t)24 * 24 * 12 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.w1r, H))) return rc;
     if ((rc = dev_alloc(ctx, &w.b1eff, H))) return rc;
     __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1};

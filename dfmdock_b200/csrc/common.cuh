@@ -71,6 +71,8 @@ struct LayerW {
   // derived (owned)
   float* T32;           // [100+P, 256] pair table, fp32
   __half* T16;          // same, fp16
+  __half* Tdrp16;       // [(z*40+d)*66+rp][256] merged dist + relpos rows (z=1: + the three zero-angle rows), fp16 of the fp32 sum
+  __half* Totp16;       // [(o*24+t)*12+p][256] merged omega + theta + phi rows
   float* w1r;           // [256] column 512 of W1, contiguous
   float* b1eff;         // [256] b1 + sym * T[166] (set per complex)
   __half* img_W1s;      // fp16 SW128 images [4 kblk][256 rows][64]

@@ -23,7 +23,8 @@ constexpr uint32_t OFF_S = W_BYTES;
 constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 4 x 256 floats of per-column parameters
 constexpr uint32_t OFF_PART = OFF_VEC + 4 * 256 * 4; // [2][128] gate partials
 constexpr uint32_t OFF_AGG = OFF_PART + 2 * 128 * 4; // [4][256] column partial sums
-constexpr uint32_t OFF_BAR = OFF_AGG + 4 * 256 * 4;  // 2 mbarriers + tmem base
+constexpr uint32_t OFF_META = OFF_AGG + 4 * 256 * 4; // [2 buffers][3][128] per-row edge metadata (neighbour, bins, radial)
+constexpr uint32_t OFF_BAR = OFF_META + 2 * 3 * 128 * 4;  // 2 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
 
@@ -77,6 +78,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// issue only (no wait): 32 consecutive columns of this thread's TMEM lane into v[0..31]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SiLU(x) * 2^-4 = h (1 + tanh(x/2)) with h = x/32: one MUFU (tanh.approx, rel. error 2^-11 -- below the fp16 operand rounding)
+__device__ __forceinline__ float silu_scaled_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float hs = x * (0.5f * S_SCALE);
+  return fmaf(hs, t, hs);
+}
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
 // 16-byte chunk `c16` (0..31) of tile row r -> byte offset inside the S tile (K-major SWIZZLE_128B)
 __device__ __forceinline__ uint32_t s_off(int r, int c16) {
   return (uint32_t)(c16 >> 3) * S_KBLK + (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
@@ -125,7 +150,8 @@ struct Params {
   LinearArgs lin;
   // EDGE / COORD
   EdgeArgs ed;
-  const __half* T16;
+  const __half* Tdrp;   // [(z*40 + d)*66 + rp][256]: T_d + T_relpos (+ the three zero-angle rows when z = 1)
+  const __half* Totp;   // [(o*24 + t)*12 + p][256]: T_omega + T_theta + T_phi
   const float* w1r;
   const float* v0;   // EDGE: b2    COORD: bc1   LINEAR: bias (or null)
   const float* v1;   // EDGE: wa    COORD: wc2
@@ -142,6 +168,9 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   float* vec2 = vec0 + 512;                                // EDGE: w1r
   float* part = reinterpret_cast<float*>(smem + OFF_PART); // [2][128]
   float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);  // [4][256]
+  int* meta_j = reinterpret_cast<int*>(smem + OFF_META);
+  uint32_t* meta_ft = reinterpret_cast<uint32_t*>(smem + OFF_META + 2 * 128 * 4);
+  float* meta_rad = reinterpret_cast<float*>(smem + OFF_META + 4 * 128 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
   const uint32_t bar0 = sbase + OFF_BAR, bar1 = sbase + OFF_BAR + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -155,6 +184,15 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
     vec0[tid] = p.v0 ? p.v0[tid] : 0.f;
     vec1[tid] = p.v1 ? p.v1[tid] : 0.f;
     vec2[tid] = (MODE == EDGE) ? p.w1r[tid] : 0.f;
+    if (MODE == EDGE && tid < 128) {   // metadata of this CTA's first tile
+      const int node0 = (int)blockIdx.x * 2 + (tid >> 6);
+      int j0 = 0; uint32_t f0 = 0; float r0 = 0.f;
+      if (node0 < p.ed.B * p.ed.N) {
+        const size_t eo = (size_t)node0 * SLOTS + (tid & 63);
+        j0 = p.ed.nbr[eo]; f0 = p.ed.feat[eo]; r0 = p.ed.radial[eo];
+      }
+      meta_j[tid] = j0; meta_ft[tid] = f0; meta_rad[tid] = r0;
+    }
   }
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -178,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   const int total_nodes = (MODE == EDGE) ? ed.B * ed.N : (MODE == COORD ? ed.B * (ed.N - ed.R) : 0);
 
   // ---------------------------------------------------------------------------------------------
-  auto build = [&](int tile) {
+  auto build = [&](int tile, int it) {
     if (MODE == LINEAR) {
       const int c16 = lane;   // this lane converts columns 8*lane .. 8*lane+7
 #pragma unroll 4
@@ -208,48 +246,92 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
         *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = v;
       }
     } else {
-      // EDGE: S = SiLU(A_i + B_j + radial*w1r + sum of 5 table rows) * 2^-4
+      // EDGE: S = SiLU(A_i + B_j + radial*w1r + T_drp[d,rp] (+ T_otp[o,t,p])) * 2^-4, one warp per row, 8 columns per lane.
+      // Rows of this warp: r = warp + 8 q, q = 0..15 (q >> 3 = residue inside the tile).  Gathers are issued a batch of
+      // four rows ahead of their use so that ~24 independent 16-byte loads per lane are in flight.
+      const int mb = it & 1;
+      const int* mj = meta_j + mb * 128;
+      const uint32_t* mft = meta_ft + mb * 128;
+      const float* mrad = meta_rad + mb * 128;
+      // prefetch the next tile's metadata (registers now, shared memory at the end of this build)
+      int nj = 0; uint32_t nft = 0; float nrad = 0.f;
+      {
+        const int ntile = tile + (int)gridDim.x;
+        const int nnode = ntile * 2 + (tid >> 6);
+        if (tid < 128 && ntile < p.ntiles && nnode < total_nodes) {
+          const size_t eo = (size_t)nnode * SLOTS + (tid & 63);
+          nj = __ldg(ed.nbr + eo); nft = __ldg(ed.feat + eo); nrad = __ldg(ed.radial + eo);
+        }
+      }
       float wr[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) wr[e] = vec2[lane * 8 + e];
       const __half* Bm = reinterpret_cast<const __half*>(ed.Bm);
-#pragma unroll
-      for (int hn = 0; hn < 2; ++hn) {
-        const int node = tile * 2 + hn;
+      struct Batch { uint4 hb[4], td[4], to[4]; float rad[4]; bool val[4], otp[4]; };
+      auto issue = [&](int bq, Batch& bt) {
+        const int node = tile * 2 + (bq >> 1);
         const bool nvalid = node < total_nodes;
-        float ai[8];
-        if (nvalid) {
-          const float4* a = reinterpret_cast<const float4*>(ed.A + (size_t)node * H + lane * 8);
-          float4 a0 = __ldg(a), a1 = __ldg(a + 1);
-          ai[0] = a0.x; ai[1] = a0.y; ai[2] = a0.z; ai[3] = a0.w; ai[4] = a1.x; ai[5] = a1.y; ai[6] = a1.z; ai[7] = a1.w;
+        const size_t brow = nvalid ? (size_t)(node / ed.N) * ed.N : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * (bq * 4 + i);
+          const bool v = nvalid && (r & 63) < ed.K;
+          const int j = v ? mj[r] : 0;
+          const uint32_t ft = v ? mft[r] : 0u;
+          const uint32_t otp = (ft >> 6) & 0x3FFFu;
+          const uint32_t drp = ((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((ft >> 20) & 127u);
+          const uint32_t oidx = (((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u);
+          bt.val[i] = v;
+          bt.otp[i] = otp != 0;
+          bt.rad[i] = mrad[r];
+          bt.hb[i] = __ldg(reinterpret_cast<const uint4*>(Bm + (brow + j) * H) + lane);
+          bt.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)drp * H) + lane);
+          bt.to[i] = make_uint4(0, 0, 0, 0);
+          if (otp != 0) bt.to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)oidx * H) + lane);
         }
-        const int b = nvalid ? node / ed.N : 0;
-#pragma unroll 2
-        for (int k = warp; k < 64; k += 8) {
-          const int r = hn * 64 + k;
+      };
+      float ai[8];
+      auto load_ai = [&](int hn) {
+        const int node = tile * 2 + hn;
+        if (node < total_nodes) {
+          const float4* a = reinterpret_cast<const float4*>(ed.A + (size_t)node * H + lane * 8);
+          const float4 a0 = __ldg(a), a1 = __ldg(a + 1);
+          ai[0] = a0.x; ai[1] = a0.y; ai[2] = a0.z; ai[3] = a0.w; ai[4] = a1.x; ai[5] = a1.y; ai[6] = a1.z; ai[7] = a1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ai[e] = 0.f;
+        }
+      };
+      auto consume = [&](int bq, const Batch& bt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * (bq * 4 + i);
           float u[8];
-          if (nvalid && k < ed.K) {
-            const size_t eo = (size_t)node * SLOTS + k;
-            const int j = __ldg(ed.nbr + eo);
-            const uint32_t ft = __ldg(ed.feat + eo);
-            const float rad = __ldg(ed.radial + eo);
-            const uint4 hb = __ldg(reinterpret_cast<const uint4*>(Bm + ((size_t)b * ed.N + j) * H) + lane);
-            const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(ft & 63u) * H) + lane);
-            const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(40u + ((ft >> 6) & 31u)) * H) + lane);
-            const uint4 t2 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(64u + ((ft >> 11) & 31u)) * H) + lane);
-            const uint4 t3 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(88u + ((ft >> 16) & 15u)) * H) + lane);
-            const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(p.T16 + (size_t)(100u + ((ft >> 20) & 127u)) * H) + lane);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = fmaf(rad, wr[e], ai[e]);
-            add_half8(u, hb); add_half8(u, t0); add_half8(u, t1); add_half8(u, t2); add_half8(u, t3); add_half8(u, t4);
+          for (int e = 0; e < 8; ++e) u[e] = fmaf(bt.rad[i], wr[e], ai[e]);
+          add_half8(u, bt.hb[i]);
+          add_half8(u, bt.td[i]);
+          add_half8(u, bt.to[i]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = silu_f(u[e]) * S_SCALE;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = 0.f;
-          }
+          for (int e = 0; e < 8; ++e) u[e] = bt.val[i] ? silu_scaled_tanh(u[e]) : 0.f;
           *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(u);
         }
+      };
+      Batch b0, b1;
+      load_ai(0);
+      issue(0, b0);
+      issue(1, b1);
+      consume(0, b0);
+      issue(2, b0);
+      consume(1, b1);
+      load_ai(1);      // rows of the second residue from here on
+      issue(3, b1);
+      consume(2, b0);
+      consume(3, b1);
+      if (tid < 128) {
+        meta_j[(mb ^ 1) * 128 + tid] = nj;
+        meta_ft[(mb ^ 1) * 128 + tid] = nft;
+        meta_rad[(mb ^ 1) * 128 + tid] = nrad;
       }
     }
   };
@@ -300,16 +382,13 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
     float m[128];
     float dotp = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32(taddr + c * 32, v);
-      const int col0 = ch * 128 + c * 32;
+    for (int c = 0; c < 4; ++c) tmem_ld32_issue(taddr + c * 32, m + c * 32);
+    tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float x = silu_f(v[e] + vec0[col0 + e]);
-        if (MODE == EDGE) m[c * 32 + e] = x;
-        dotp = fmaf(x, vec1[col0 + e], dotp);
-      }
+    for (int e = 0; e < 128; ++e) {
+      const float x = silu_fast(m[e] + vec0[ch * 128 + e]);
+      m[e] = x;
+      dotp = fmaf(x, vec1[ch * 128 + e], dotp);
     }
     tc_fence_before();
     part[ch * 128 + erow] = dotp;
@@ -347,7 +426,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
       return;
     }
     // EDGE: gate, optional m* spill for the coordinate head, segment sum over the residue's rows
-    const float g = valid ? 1.f / (1.f + __expf(-(tot + p.ba[0]))) : 0.f;
+    const float g = valid ? __fdividef(1.f, 1.f + __expf(-(tot + p.ba[0]))) : 0.f;
 #pragma unroll
     for (int e = 0; e < 128; ++e) m[e] *= g;
     if (ed.last && valid) {
@@ -385,7 +464,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   int it = 0, prev_tile = -1;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    build(tile);
+    build(tile, it);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -456,7 +535,8 @@ int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   p.ntiles = (a.B * a.N + 1) / 2;
   p.Wimg = w.img_W2;
   p.ed = a;
-  p.T16 = w.T16;
+  p.Tdrp = w.Tdrp16;
+  p.Totp = w.Totp16;
   p.w1r = w.w1r;
   p.v0 = w.b2;
   p.v1 = w.wa;

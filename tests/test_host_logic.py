@@ -1,0 +1,148 @@
+"""CPU: host-side logic -- C-ABI surface, checkpoint reader, feature builder, trajectory sharding (gloo, world size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dfmdock_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dfmdock_b200.h")).read()
+    declared = set(re.findall(r"\b(dfm_[a-z_0-9]+)\s*\(", header)) - {"dfm_ctx"}
+    assert len(declared) >= 18
+    lib = _lib.load()                      # symbols only; no GPU needed
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert b"sm_100a" in lib.dfm_version()
+
+
+def test_no_cpu_fallback_and_product_never_imports_oracle():
+    from dfmdock_b200 import Score_Model
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    m = Score_Model(synthetic_state_dict(0), synthetic_hparams())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.to("cpu")
+    with pytest.raises(RuntimeError):
+        m.score(torch.zeros(1, 3, 3, 3), torch.zeros(1))
+    pkg = os.path.join(ROOT, "dfmdock_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_lightning_checkpoint_roundtrip(tmp_path):
+    from dfmdock_b200.checkpoint import load_checkpoint
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict, write_lightning_ckpt
+    sd, hp = synthetic_state_dict(3, 67), synthetic_hparams(67)
+    p = str(tmp_path / "model.ckpt")
+    write_lightning_ckpt(p, sd, hp)
+    sd2, hp2 = load_checkpoint(p)
+    assert set(sd2) == set(sd) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert hp2["model"]["positional_embed_dim"] == 67 and hp2["diffuser"]["so3"]["max_sigma"] == 1.5
+    with pytest.raises(KeyError):
+        torch.save({"weights": 1}, p)
+        load_checkpoint(p)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/weights/pinder_0.ckpt"), reason="reference tree not mounted")
+def test_shipped_checkpoints_load_unchanged_without_omegaconf():
+    from dfmdock_b200.checkpoint import load_checkpoint, load_db5_record
+    for path, width in (("/root/reference/weights/pinder_0.ckpt", 67), ("/root/reference/checkpoints/dips/model_0.ckpt", 66)):
+        sd, hp = load_checkpoint(path)
+        assert len(sd) == 104 and sd["positional_embed.weight"].shape == (128, width)
+        assert hp["model"]["node_dim"] == 256 and hp["model"]["cut_off"] == 20.0 and hp["diffuser"]["r3"]["max_sigma"] == 30.0
+    assert "omegaconf" not in sys.modules or getattr(sys.modules["omegaconf"], "__file__", None) is None
+    rec = load_db5_record("/root/reference/data/db5_test/1QA9.pt")
+    assert rec["receptor"]["x"].shape == (102, 1280) and rec["ligand"]["pos"].shape == (95, 3, 3)
+
+
+def test_features_match_oracle_relpos_and_onehot():
+    from dfmdock_b200.features import get_position_matrix, relpos_bins, sequence_to_onehot, synthetic_complex
+    from oracle import dfmdock_oracle as orc
+    assert torch.equal(relpos_bins(7, 5), orc.relpos_bins(7, 5))
+    assert torch.equal(get_position_matrix(40, 30, 67, 1.0), orc.position_matrix(40, 30, 67, 1.0))
+    oh = sequence_to_onehot("ACDXZ")
+    assert oh.shape == (5, 21) and oh[0, 0] == 1 and oh[3, 20] == 1 and oh[4, 20] == 1
+    a, b = synthetic_complex(10, 8, seed=1), synthetic_complex(10, 8, seed=1)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    ca = a["rec_pos"][:, 1]
+    assert torch.allclose((ca[1:] - ca[:-1]).norm(dim=-1), torch.full((9,), 3.8), atol=1e-4)
+
+
+def test_diffusers_match_oracle_schedules():
+    from dfmdock_b200.diffusers import R3Diffuser, SO3Diffuser
+    from oracle import dfmdock_oracle as orc
+    so3 = SO3Diffuser({"min_sigma": 0.1, "max_sigma": 1.5, "schedule": "logarithmic"})
+    r3 = R3Diffuser({"min_sigma": 0.1, "max_sigma": 30.0})
+    for t in (1.0, 0.5, 1e-3):
+        assert so3.diffusion_coef(t) == orc.so3_g(t) and r3.diffusion_coef(t) == orc.r3_g(t)
+    torch.manual_seed(0)
+    a = so3.torch_reverse(torch.ones(1, 3), torch.tensor(0.025), 0.5, noise_scale=0.5)
+    torch.manual_seed(0)
+    z = 0.5 * torch.randn(1, 3)
+    b = orc.reverse_increment(orc.so3_g(0.5), torch.ones(1, 3), torch.tensor(0.025), z)
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        so3.torch_reverse(torch.ones(1, 3), torch.tensor(0.1), torch.tensor([0.5]))
+
+
+def test_shard_range_is_a_balanced_partition():
+    from dfmdock_b200.distributed import shard_range
+    for total in (0, 1, 5, 40, 256, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DFM_ROOT"])
+from dfmdock_b200.distributed import gather_rows, shard_range, rank_world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["DFM_PORT"], rank=int(os.environ["RANK"]), world_size=2)
+rank, world = rank_world()
+total = 7                                     # ragged: 4 + 3
+lo, hi = shard_range(total, rank, world)
+full_truth = torch.arange(total * 8, dtype=torch.float32).view(total, 8)
+out = gather_rows(full_truth[lo:hi].clone(), total)
+assert torch.equal(out, full_truth), (rank, out)
+best = int(torch.argmin(out[:, 6]))
+assert best == 0
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gather_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), DFM_ROOT=ROOT, DFM_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_bench_roofline_arithmetic():
+    sys.path.insert(0, ROOT)
+    import bench
+    # 11.66 / 17.76 / 47.36 GFLOP per pose-step at N = 197 / 300 / 800
+    for n, gf in ((197, 11.66), (300, 17.76), (800, 47.36)):
+        assert abs(bench.algorithmic_flops_per_pose_step(n) / 1e9 - gf) < 0.02
+    assert bench.edge_kernel_flops_per_launch(256, 300) == 2 * 4608000 * 65536 + 2 * 4608000 * 256
