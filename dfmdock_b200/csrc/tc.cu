@@ -9,6 +9,8 @@
 // fp32 accumulation; operand scaling by exact powers of two keeps fp16 in range (common.cuh).
 //
 //   D[128 x 256] (TMEM, lane = row, column = feature) = S[128 x 256] (smem) * W[256 x 256]^T (smem)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tc {
@@ -100,6 +102,22 @@ __device__ __forceinline__ float silu_scaled_tanh(float x) {
   const float hs = x * (0.5f * S_SCALE);
   return fmaf(hs, t, hs);
 }
+// packed variant: two SiLU(x) * 2^-4 results straight into the fp16 operand (tanh.approx.f16x2: one MUFU per pair)
+__device__ __forceinline__ uint32_t silu_scaled_tanh_h2(float x0, float x1) {
+  const __half2 xh = __floats2half2_rn(0.5f * x0, 0.5f * x1);
+  uint32_t xi = *reinterpret_cast<const uint32_t*>(&xh), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(xi));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hs = __hmul2(xh, __float2half2_rn(2.0f * S_SCALE));
+  const __half2 o = __hfma2(hs, t, hs);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  const float h = 0.5f * x;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 // 16-byte chunk `c16` (0..31) of tile row r -> byte offset inside the S tile (K-major SWIZZLE_128B)
@@ -158,7 +176,8 @@ struct Params {
   const float* ba;   // EDGE: att bias
 };
 
-template <int MODE>
+// VAR (EDGE only): bit 0 = build SiLU in packed half2, bit 1 = tanh-based SiLU in the epilogue
+template <int MODE, int VAR = 0>
 __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -309,12 +328,26 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
           float u[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) u[e] = fmaf(bt.rad[i], wr[e], ai[e]);
-          add_half8(u, bt.hb[i]);
-          add_half8(u, bt.td[i]);
-          add_half8(u, bt.to[i]);
+          if (VAR & 1) {
+            // gathered fp16 rows are summed as packed halves (3 terms), then joined with the fp32 part
+            const __half2* hb = reinterpret_cast<const __half2*>(&bt.hb[i]);
+            const __half2* td = reinterpret_cast<const __half2*>(&bt.td[i]);
+            const __half2* to = reinterpret_cast<const __half2*>(&bt.to[i]);
+            uint32_t o4[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = bt.val[i] ? silu_scaled_tanh(u[e]) : 0.f;
-          *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(u);
+            for (int q2 = 0; q2 < 4; ++q2) {
+              const float2 g = __half22float2(__hadd2(__hadd2(hb[q2], td[q2]), to[q2]));
+              o4[q2] = bt.val[i] ? silu_scaled_tanh_h2(u[2 * q2] + g.x, u[2 * q2 + 1] + g.y) : 0u;
+            }
+            *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          } else {
+            add_half8(u, bt.hb[i]);
+            add_half8(u, bt.td[i]);
+            add_half8(u, bt.to[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = bt.val[i] ? silu_scaled_tanh(u[e]) : 0.f;
+            *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(u);
+          }
         }
       };
       Batch b0, b1;
@@ -386,7 +419,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
     tmem_ld_wait();
 #pragma unroll
     for (int e = 0; e < 128; ++e) {
-      const float x = silu_fast(m[e] + vec0[ch * 128 + e]);
+      const float x = (VAR & 2) ? silu_tanh(m[e] + vec0[ch * 128 + e]) : silu_fast(m[e] + vec0[ch * 128 + e]);
       m[e] = x;
       dotp = fmaf(x, vec1[ch * 128 + e], dotp);
     }
@@ -502,16 +535,16 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   }
 }
 
-template <int MODE>
+template <int MODE, int VAR = 0>
 static int launch(dfm_ctx* ctx, const Params& p, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(k_tc<MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
     attr = true;
   }
   const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;
-  k_tc<MODE><<<grid, 256, SMEM_ALLOC, s>>>(p);
+  k_tc<MODE, VAR><<<grid, 256, SMEM_ALLOC, s>>>(p);
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -541,7 +574,17 @@ int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   p.v0 = w.b2;
   p.v1 = w.wa;
   p.ba = w.ba;
-  return tc::launch<tc::EDGE>(ctx, p, s);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("DFM_EDGE_VARIANT");
+    variant = e ? atoi(e) : 3;
+  }
+  switch (variant) {
+    case 0: return tc::launch<tc::EDGE, 0>(ctx, p, s);
+    case 1: return tc::launch<tc::EDGE, 1>(ctx, p, s);
+    case 2: return tc::launch<tc::EDGE, 2>(ctx, p, s);
+    default: return tc::launch<tc::EDGE, 3>(ctx, p, s);
+  }
 }
 
 int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
