@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t silu_scaled_tanh_h2(float x0, float x1) {
   uint32_t xi = *reinterpret_cast<const uint32_t*>(&xh), ti;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(xi));
   const __half2 t = *reinterpret_cast<const __half2*>(&ti);
-  const __half2 hs = __hmul2(xh, __float2half2_rn(2.0f * S_SCALE));
+  const __half2 hs = __hmul2(xh, __float2half2_rn(S_SCALE));   // (x/2) * 2^-4 = x/32
   const __half2 o = __hfma2(hs, t, hs);
   return *reinterpret_cast<const uint32_t*>(&o);
 }
