@@ -23,8 +23,8 @@ constexpr uint32_t S_KBLK = TILE_M * 128;
 constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_S = W_BYTES;
 constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 4 x 256 floats of per-column parameters
-constexpr uint32_t OFF_PART = OFF_VEC + 4 * 256 * 4; // [2][128] gate partials
-constexpr uint32_t OFF_AGG = OFF_PART + 2 * 128 * 4; // [4][256] column partial sums
+constexpr uint32_t OFF_PART = OFF_VEC + 4 * 256 * 4; // [4][128] gate partials
+constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [4][256] column partial sums
 constexpr uint32_t OFF_META = OFF_AGG + 4 * 256 * 4; // [2 buffers][3][128] per-row edge metadata (neighbour, bins, radial)
 constexpr uint32_t OFF_BAR = OFF_META + 2 * 3 * 128 * 4;  // 2 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
@@ -144,7 +144,7 @@ __device__ __forceinline__ void add_half8(float (&u)[8], uint4 h) {
 }
 
 // 32 lanes x 32 values -> lane l ends with sum over lanes of v[l]   (31 shuffles)
-__device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
+__device__ __forceinline__ float lane_transpose_sum(float* v, int lane) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     const bool up = (lane & o) != 0;
@@ -176,17 +176,21 @@ struct Params {
   const float* ba;   // EDGE: att bias
 };
 
-// VAR (EDGE only): bit 0 = build SiLU in packed half2, bit 1 = tanh-based SiLU in the epilogue
+constexpr int NT = 512;            // threads per CTA: 16 warps = 4 TMEM lane quarters x 4 column quarters
+constexpr int NWARP = NT / 32;
+constexpr int CW = 256 / (NWARP / 4);   // accumulator columns per thread in the epilogue (64)
+
+// VAR (EDGE only): bit 0 = build SiLU in packed half2 (less accurate, kept for experiments)
 template <int MODE, int VAR = 0>
-__global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
+__global__ void __launch_bounds__(NT, 1) k_tc(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* vec0 = reinterpret_cast<float*>(smem + OFF_VEC);
   float* vec1 = vec0 + 256;
   float* vec2 = vec0 + 512;                                // EDGE: w1r
-  float* part = reinterpret_cast<float*>(smem + OFF_PART); // [2][128]
-  float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);  // [4][256]
+  float* part = reinterpret_cast<float*>(smem + OFF_PART); // [4][128] gate partials (one per column quarter)
+  float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);  // [4][256] column sums per lane quarter
   int* meta_j = reinterpret_cast<int*>(smem + OFF_META);
   uint32_t* meta_ft = reinterpret_cast<uint32_t*>(smem + OFF_META + 2 * 128 * 4);
   float* meta_rad = reinterpret_cast<float*>(smem + OFF_META + 4 * 128 * 4);
@@ -198,11 +202,13 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.Wimg);
     uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
-#pragma unroll 8
-    for (int i = tid; i < (int)(W_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
-    vec0[tid] = p.v0 ? p.v0[tid] : 0.f;
-    vec1[tid] = p.v1 ? p.v1[tid] : 0.f;
-    vec2[tid] = (MODE == EDGE) ? p.w1r[tid] : 0.f;
+#pragma unroll 4
+    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
+    if (tid < 256) {
+      vec0[tid] = p.v0 ? p.v0[tid] : 0.f;
+      vec1[tid] = p.v1 ? p.v1[tid] : 0.f;
+      vec2[tid] = (MODE == EDGE) ? p.w1r[tid] : 0.f;
+    }
     if (MODE == EDGE && tid < 128) {   // metadata of this CTA's first tile
       const int node0 = (int)blockIdx.x * 2 + (tid >> 6);
       int j0 = 0; uint32_t f0 = 0; float r0 = 0.f;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int q = warp & 3, ch = warp >> 2;       // epilogue: TMEM lane quarter / column half
+  const int q = warp & 3, cq = warp >> 2;       // epilogue: TMEM lane quarter / column quarter
   const int erow = q * 32 + lane;               // tile row owned in the epilogue
 
   const EdgeArgs& ed = p.ed;
@@ -237,9 +243,8 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
   // ---------------------------------------------------------------------------------------------
   auto build = [&](int tile, int it) {
     if (MODE == LINEAR) {
-      const int c16 = lane;   // this lane converts columns 8*lane .. 8*lane+7
 #pragma unroll 4
-      for (int r = warp; r < TILE_M; r += 8) {
+      for (int r = warp; r < TILE_M; r += NWARP) {
         const int m = tile * TILE_M + r;
         float x[8];
         if (m < p.lin.M) {
@@ -252,12 +257,12 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) x[e] = 0.f;
         }
-        *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, c16)) = pack8(x);
+        *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(x);
       }
     } else if (MODE == COORD) {
       // rows are contiguous fp16 in mstar: node pair `tile`, 64 slots each
 #pragma unroll 4
-      for (int r = warp; r < TILE_M; r += 8) {
+      for (int r = warp; r < TILE_M; r += NWARP) {
         const int node = tile * 2 + (r >> 6);
         uint4 v = make_uint4(0, 0, 0, 0);
         if (node < total_nodes)
@@ -266,8 +271,8 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
       }
     } else {
       // EDGE: S = SiLU(A_i + B_j + radial*w1r + T_drp[d,rp] (+ T_otp[o,t,p])) * 2^-4, one warp per row, 8 columns per lane.
-      // Rows of this warp: r = warp + 8 q, q = 0..15 (q >> 3 = residue inside the tile).  Gathers are issued a batch of
-      // four rows ahead of their use so that ~24 independent 16-byte loads per lane are in flight.
+      // Rows of this warp: r = warp + 16 q, q = 0..7 (q >> 2 = residue inside the tile).  The gathers of four rows are
+      // issued together (12 independent 16-byte loads per lane) before any of them is consumed.
       const int mb = it & 1;
       const int* mj = meta_j + mb * 128;
       const uint32_t* mft = meta_ft + mb * 128;
@@ -283,36 +288,18 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
         }
       }
       float wr[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) wr[e] = vec2[lane * 8 + e];
+      {
+        const float4 w0 = *reinterpret_cast<const float4*>(vec2 + lane * 8), w1 = *reinterpret_cast<const float4*>(vec2 + lane * 8 + 4);
+        wr[0] = w0.x; wr[1] = w0.y; wr[2] = w0.z; wr[3] = w0.w; wr[4] = w1.x; wr[5] = w1.y; wr[6] = w1.z; wr[7] = w1.w;
+      }
       const __half* Bm = reinterpret_cast<const __half*>(ed.Bm);
-      struct Batch { uint4 hb[4], td[4], to[4]; float rad[4]; bool val[4], otp[4]; };
-      auto issue = [&](int bq, Batch& bt) {
-        const int node = tile * 2 + (bq >> 1);
+#pragma unroll
+      for (int hn = 0; hn < 2; ++hn) {
+        const int node = tile * 2 + hn;
         const bool nvalid = node < total_nodes;
         const size_t brow = nvalid ? (size_t)(node / ed.N) * ed.N : 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = warp + 8 * (bq * 4 + i);
-          const bool v = nvalid && (r & 63) < ed.K;
-          const int j = v ? mj[r] : 0;
-          const uint32_t ft = v ? mft[r] : 0u;
-          const uint32_t otp = (ft >> 6) & 0x3FFFu;
-          const uint32_t drp = ((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((ft >> 20) & 127u);
-          const uint32_t oidx = (((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u);
-          bt.val[i] = v;
-          bt.otp[i] = otp != 0;
-          bt.rad[i] = mrad[r];
-          bt.hb[i] = __ldg(reinterpret_cast<const uint4*>(Bm + (brow + j) * H) + lane);
-          bt.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)drp * H) + lane);
-          bt.to[i] = make_uint4(0, 0, 0, 0);
-          if (otp != 0) bt.to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)oidx * H) + lane);
-        }
-      };
-      float ai[8];
-      auto load_ai = [&](int hn) {
-        const int node = tile * 2 + hn;
-        if (node < total_nodes) {
+        float ai[8];
+        if (nvalid) {
           const float4* a = reinterpret_cast<const float4*>(ed.A + (size_t)node * H + lane * 8);
           const float4 a0 = __ldg(a), a1 = __ldg(a + 1);
           ai[0] = a0.x; ai[1] = a0.y; ai[2] = a0.z; ai[3] = a0.w; ai[4] = a1.x; ai[5] = a1.y; ai[6] = a1.z; ai[7] = a1.w;
@@ -320,47 +307,52 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) ai[e] = 0.f;
         }
-      };
-      auto consume = [&](int bq, const Batch& bt) {
+        uint4 hb[4], td[4], to[4];
+        float rad[4];
+        bool val[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = warp + 8 * (bq * 4 + i);
+          const int r = warp + NWARP * (hn * 4 + i);
+          const bool v = nvalid && (r & 63) < ed.K;
+          const int j = v ? mj[r] : 0;
+          const uint32_t ft = v ? mft[r] : 0u;
+          const uint32_t otp = (ft >> 6) & 0x3FFFu;
+          const uint32_t drp = ((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((ft >> 20) & 127u);
+          const uint32_t oidx = (((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u);
+          val[i] = v;
+          rad[i] = mrad[r];
+          hb[i] = __ldg(reinterpret_cast<const uint4*>(Bm + (brow + j) * H) + lane);
+          td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)drp * H) + lane);
+          to[i] = make_uint4(0, 0, 0, 0);
+          if (otp != 0) to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)oidx * H) + lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + NWARP * (hn * 4 + i);
           float u[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = fmaf(bt.rad[i], wr[e], ai[e]);
+          for (int e = 0; e < 8; ++e) u[e] = fmaf(rad[i], wr[e], ai[e]);
           if (VAR & 1) {
-            // gathered fp16 rows are summed as packed halves (3 terms), then joined with the fp32 part
-            const __half2* hb = reinterpret_cast<const __half2*>(&bt.hb[i]);
-            const __half2* td = reinterpret_cast<const __half2*>(&bt.td[i]);
-            const __half2* to = reinterpret_cast<const __half2*>(&bt.to[i]);
+            const __half2* hbp = reinterpret_cast<const __half2*>(&hb[i]);
+            const __half2* tdp = reinterpret_cast<const __half2*>(&td[i]);
+            const __half2* top = reinterpret_cast<const __half2*>(&to[i]);
             uint32_t o4[4];
 #pragma unroll
             for (int q2 = 0; q2 < 4; ++q2) {
-              const float2 g = __half22float2(__hadd2(__hadd2(hb[q2], td[q2]), to[q2]));
-              o4[q2] = bt.val[i] ? silu_scaled_tanh_h2(u[2 * q2] + g.x, u[2 * q2 + 1] + g.y) : 0u;
+              const float2 g = __half22float2(__hadd2(__hadd2(hbp[q2], tdp[q2]), top[q2]));
+              o4[q2] = val[i] ? silu_scaled_tanh_h2(u[2 * q2] + g.x, u[2 * q2 + 1] + g.y) : 0u;
             }
             *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
           } else {
-            add_half8(u, bt.hb[i]);
-            add_half8(u, bt.td[i]);
-            add_half8(u, bt.to[i]);
+            add_half8(u, hb[i]);
+            add_half8(u, td[i]);
+            add_half8(u, to[i]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = bt.val[i] ? silu_scaled_tanh(u[e]) : 0.f;
+            for (int e = 0; e < 8; ++e) u[e] = val[i] ? silu_scaled_tanh(u[e]) : 0.f;
             *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(u);
           }
         }
-      };
-      Batch b0, b1;
-      load_ai(0);
-      issue(0, b0);
-      issue(1, b1);
-      consume(0, b0);
-      issue(2, b0);
-      consume(1, b1);
-      load_ai(1);      // rows of the second residue from here on
-      issue(3, b1);
-      consume(2, b0);
-      consume(3, b1);
+      }
       if (tid < 128) {
         meta_j[(mb ^ 1) * 128 + tid] = nj;
         meta_ft[(mb ^ 1) * 128 + tid] = nft;
@@ -371,66 +363,60 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
 
   // ---------------------------------------------------------------------------------------------
   auto epilogue = [&](int tile, int buf) {
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cq * CW);
+    float m[CW];
+#pragma unroll
+    for (int c = 0; c < CW / 32; ++c) tmem_ld32_issue(taddr + c * 32, m + c * 32);
+    tmem_ld_wait();
+    tc_fence_before();
     if (MODE == LINEAR) {
-      const int m = tile * TILE_M + erow;
+      const int mrow = tile * TILE_M + erow;
+      if (mrow < p.lin.M) {
+        const int col0 = cq * CW;
+        const size_t o = (size_t)mrow * H + col0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        if (m < p.lin.M) {
-          const int col0 = ch * 128 + c * 32;
-          const size_t o = (size_t)m * H + col0;
+        for (int e = 0; e < CW; ++e) m[e] += vec0[col0 + e];
+        if (p.lin.add) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += vec0[col0 + e];
-          if (p.lin.add) {
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 ad = *reinterpret_cast<const float4*>(p.lin.add + o + e4 * 4);
-              v[e4 * 4] += ad.x; v[e4 * 4 + 1] += ad.y; v[e4 * 4 + 2] += ad.z; v[e4 * 4 + 3] += ad.w;
-            }
+          for (int e4 = 0; e4 < CW / 4; ++e4) {
+            const float4 ad = *reinterpret_cast<const float4*>(p.lin.add + o + e4 * 4);
+            m[e4 * 4] += ad.x; m[e4 * 4 + 1] += ad.y; m[e4 * 4 + 2] += ad.z; m[e4 * 4 + 3] += ad.w;
           }
-          if (p.lin.out) {
+        }
+        if (p.lin.out) {
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4)
-              *reinterpret_cast<float4*>(p.lin.out + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-          }
-          if (p.lin.out16) {
+          for (int e4 = 0; e4 < CW / 4; ++e4)
+            *reinterpret_cast<float4*>(p.lin.out + o + e4 * 4) = make_float4(m[e4 * 4], m[e4 * 4 + 1], m[e4 * 4 + 2], m[e4 * 4 + 3]);
+        }
+        if (p.lin.out16) {
 #pragma unroll
-            for (int e8 = 0; e8 < 4; ++e8) {
-              float x8[8];
+          for (int e8 = 0; e8 < CW / 8; ++e8) {
+            float x8[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x8[e] = v[e8 * 8 + e];
-              *reinterpret_cast<uint4*>(p.lin.out16 + o + e8 * 8) = pack8(x8);
-            }
+            for (int e = 0; e < 8; ++e) x8[e] = m[e8 * 8 + e];
+            *reinterpret_cast<uint4*>(p.lin.out16 + o + e8 * 8) = pack8(x8);
           }
         }
       }
-      tc_fence_before();
       return;
     }
     const int hn = erow >> 6, k = erow & 63;
     const int node = tile * 2 + hn;
     const bool valid = node < total_nodes && k < ed.K;
-    float m[128];
     float dotp = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld32_issue(taddr + c * 32, m + c * 32);
-    tmem_ld_wait();
-#pragma unroll
-    for (int e = 0; e < 128; ++e) {
-      const float x = (VAR & 2) ? silu_tanh(m[e] + vec0[ch * 128 + e]) : silu_fast(m[e] + vec0[ch * 128 + e]);
+    for (int e = 0; e < CW; ++e) {
+      const float x = silu_tanh(m[e] + vec0[cq * CW + e]);
       m[e] = x;
-      dotp = fmaf(x, vec1[ch * 128 + e], dotp);
+      dotp = fmaf(x, vec1[cq * CW + e], dotp);
     }
-    tc_fence_before();
-    part[ch * 128 + erow] = dotp;
+    part[cq * 128 + erow] = dotp;
     __syncthreads();
-    const float tot = part[erow] + part[128 + erow];
+    const float tot = part[erow] + part[128 + erow] + part[256 + erow] + part[384 + erow];
     if (MODE == COORD) {
       // coordinate displacement of ligand residue `node` (index over B*L): mean_k diffn_k * clamp(w_k, +-2)
       float fx = 0.f, fy = 0.f, fz = 0.f;
-      if (valid && ch == 0) {
+      if (valid && cq == 0) {
         const int L = ed.N - ed.R;
         const int b = node / L, i = ed.R + node % L;
         const size_t gi = (size_t)b * ed.N + i;
@@ -443,7 +429,7 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
         fx = dx * sc; fy = dy * sc; fz = dz * sc;
       }
       fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-      if (ch == 0 && lane == 0) { aggp[q * 4] = fx; aggp[q * 4 + 1] = fy; aggp[q * 4 + 2] = fz; }
+      if (cq == 0 && lane == 0) { aggp[q * 4] = fx; aggp[q * 4 + 1] = fy; aggp[q * 4 + 2] = fz; }
       __syncthreads();
       if (tid < 2) {
         const int nd = tile * 2 + tid;
@@ -461,13 +447,13 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
     // EDGE: gate, optional m* spill for the coordinate head, segment sum over the residue's rows
     const float g = valid ? __fdividef(1.f, 1.f + __expf(-(tot + p.ba[0]))) : 0.f;
 #pragma unroll
-    for (int e = 0; e < 128; ++e) m[e] *= g;
+    for (int e = 0; e < CW; ++e) m[e] *= g;
     if (ed.last && valid) {
       const int b = node / ed.N, i = node % ed.N;
       if (i >= ed.R) {
-        __half* dst = ed.mstar + (((size_t)b * (ed.N - ed.R) + (i - ed.R)) * SLOTS + k) * H + ch * 128;
+        __half* dst = ed.mstar + (((size_t)b * (ed.N - ed.R) + (i - ed.R)) * SLOTS + k) * H + cq * CW;
 #pragma unroll
-        for (int e8 = 0; e8 < 16; ++e8) {
+        for (int e8 = 0; e8 < CW / 8; ++e8) {
           float x8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) x8[e] = m[e8 * 8 + e] * S_SCALE;
@@ -476,18 +462,17 @@ __global__ void __launch_bounds__(256, 1) k_tc(const Params p) {
       }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = m[c * 32 + e];
-      const float cs = lane_transpose_sum(v, lane);
-      aggp[q * 256 + ch * 128 + c * 32 + lane] = cs;
+    for (int c = 0; c < CW / 32; ++c) {
+      const float cs = lane_transpose_sum(m + c * 32, lane);
+      aggp[q * 256 + cq * CW + c * 32 + lane] = cs;
     }
     __syncthreads();
+    if (tid < 256) {
 #pragma unroll
-    for (int hn2 = 0; hn2 < 2; ++hn2) {
-      const int nd = tile * 2 + hn2;
-      if (nd < total_nodes) ed.agg[(size_t)nd * H + tid] = aggp[(2 * hn2) * 256 + tid] + aggp[(2 * hn2 + 1) * 256 + tid];
+      for (int hn2 = 0; hn2 < 2; ++hn2) {
+        const int nd = tile * 2 + hn2;
+        if (nd < total_nodes) ed.agg[(size_t)nd * H + tid] = aggp[(2 * hn2) * 256 + tid] + aggp[(2 * hn2 + 1) * 256 + tid];
+      }
     }
   };
 
@@ -544,7 +529,7 @@ static int launch(dfm_ctx* ctx, const Params& p, cudaStream_t s) {
   }
   const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;
-  k_tc<MODE, VAR><<<grid, 256, SMEM_ALLOC, s>>>(p);
+  k_tc<MODE, VAR><<<grid, NT, SMEM_ALLOC, s>>>(p);
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -577,14 +562,10 @@ int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("DFM_EDGE_VARIANT");
-    variant = e ? atoi(e) : 3;
+    variant = e ? atoi(e) : 0;
   }
-  switch (variant) {
-    case 0: return tc::launch<tc::EDGE, 0>(ctx, p, s);
-    case 1: return tc::launch<tc::EDGE, 1>(ctx, p, s);
-    case 2: return tc::launch<tc::EDGE, 2>(ctx, p, s);
-    default: return tc::launch<tc::EDGE, 3>(ctx, p, s);
-  }
+  if (variant == 1) return tc::launch<tc::EDGE, 1>(ctx, p, s);
+  return tc::launch<tc::EDGE, 0>(ctx, p, s);
 }
 
 int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
