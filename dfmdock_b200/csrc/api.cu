@@ -1,6 +1,7 @@
 // C ABI (include/dfmdock_b200.h): context, weight repacking, the forward pass schedule and the sampler loop.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -52,6 +53,7 @@ Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base) {
   w.fbuf = (float*)take(b * L * 4 * 4);
   w.esum = (float*)take(b * R * 4 * 4);
   w.tsc = (float*)take(b * 8 * 4);
+  w.emeta = (int4*)take(b * N * SLOTS * 16);
   w.bytes = off;
   return w;
 }
@@ -83,6 +85,7 @@ extern "C" int dfm_create(dfm_ctx** out, int device) {
   dfm_ctx* c = new dfm_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("DFM_EDGE_KERNEL")) c->edge_kernel = atoi(e);
   if (dfm_upload_bin_edges() != 0) {
     delete c;
     dfm_set_error("dfm_create: cannot upload bin edges");
@@ -185,9 +188,12 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = dev_alloc(ctx, &w.T16, trows * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.Tdrp16, (size_t)2 * 40 * 66 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.Totp16, (size_t)24 * 24 * 12 * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.Tdrp16h, (size_t)2 * 40 * 66 * H))) return rc;
+    if ((rc = dev_alloc(ctx, &w.Totp16h, (size_t)24 * 24 * 12 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.w1r, H))) return rc;
     if ((rc = dev_alloc(ctx, &w.b1eff, H))) return rc;
-    __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1};
+    __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1, &w.img_W2h,
+                       &w.img_Wc1s};
     for (auto pp : imgs) if ((rc = dev_alloc(ctx, pp, (size_t)H * H))) return rc;
     if ((rc = launch_pair_table(ctx, l, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W1, 641, 0, 1.f, w.img_W1s, s))) return rc;
@@ -197,6 +203,8 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = launch_image_pack(ctx, w.W3, 512, 256, AGG_UNSCALE, w.img_W3a, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W4, 256, 0, 1.f, w.img_W4, s))) return rc;
     if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, S_UNSCALE, w.img_Wc1, s))) return rc;
+    if ((rc = launch_image_pack(ctx, w.W2, 256, 0, 0.5f, w.img_W2h, s))) return rc;
+    if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, 64.f, w.img_Wc1s, s))) return rc;
   }
   NEED("to_energy.0.weight", {H, 2 * H}); ctx->We = tmp;
   NEED("to_energy.1.weight", {H}); ctx->e_ln_w = tmp;
@@ -299,24 +307,32 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
   for (int l = 0; l < DFM_DEPTH; ++l) {
     const LayerW& w = ctx->layer[l];
     const bool last = l == DFM_DEPTH - 1;
+    const bool ews = !fp32 && ctx->edge_kernel == 1;
+    __half* Ahi = reinterpret_cast<__half*>(ws.A);
+    __half* Alo = Ahi + (size_t)M * H;
     LinearArgs la{};
     la.A = ws.h; la.a_scale = 1.f; la.M = M;
     // A = W1s h + b1
     la.W32 = w.W1; la.ldw = 641; la.w_col0 = 0; la.Wimg = w.img_W1s; la.bias = w.b1eff; la.add = nullptr;
     la.out = ws.A; la.out16 = nullptr;
+    if (ews) { la.out = nullptr; la.out16 = Ahi; la.out16_lo = Alo; la.out_scale = 0.5f; }
     if ((rc = linear(ctx, fp32, la, s))) return rc;
     // Bm = W1d h
-    la.w_col0 = 256; la.Wimg = w.img_W1d; la.bias = nullptr;
+    la.w_col0 = 256; la.Wimg = w.img_W1d; la.bias = nullptr; la.out16_lo = nullptr;
     if (fp32) { la.out = ws.Bm; la.out16 = nullptr; } else { la.out = nullptr; la.out16 = reinterpret_cast<__half*>(ws.Bm); }
     if ((rc = linear(ctx, fp32, la, s))) return rc;
+    la.out_scale = 0.f;
     EdgeArgs ea{};
     ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
     ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
     const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
     if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
+    if (ews) ea.coord_img = w.img_Wc1s;
     if (fp32) {
       if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
+    } else if (ews) {
+      if ((rc = launch_edge_ws(ctx, ea, ws.emeta, Ahi, Alo, s))) return rc;
     } else {
       if ((rc = launch_edge_tc(ctx, ea, s))) return rc;
     }

@@ -82,6 +82,11 @@ struct LayerW {
   __half* img_W3a;      // x 2^6
   __half* img_W4;
   __half* img_Wc1;      // x 2^4
+  // operands of the warp-specialised edge kernel (edge_ws.cu): everything pre-halved
+  __half* Tdrp16h;      // Tdrp16 / 2
+  __half* Totp16h;      // Totp16 / 2
+  __half* img_W2h;      // W2 / 2
+  __half* img_Wc1s;     // Wc1 x 2^6 (gated messages are spilled x 2^-6)
 };
 
 struct dfm_ctx {
@@ -114,6 +119,7 @@ struct dfm_ctx {
   size_t h0_cap = 0, rec_cap = 0;
   uint64_t launches = 0;
   int num_sms = 148;
+  int edge_kernel = 1;        // 1 = warp-specialised half2 kernel (edge_ws.cu), 0 = v1 (tc.cu k_tc<EDGE>); env DFM_EDGE_KERNEL
   // optional CUDA-event timing of the dominant (edge) kernel, for bench.py's roofline line
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
@@ -140,6 +146,7 @@ struct Workspace {
   float* fbuf;       // [B,L,4]
   float* esum;       // [B,R,2]
   float* tsc;        // [B,8] tr_score(3) rot_score(3) scratch when the caller passes NULL
+  int4* emeta;       // [B,N,64] {global row of j, Tdrp row, Totp row or -1, radial bits} (edge_ws.cu)
   size_t bytes;
 };
 
@@ -156,7 +163,9 @@ struct LinearArgs {
   const float* bias;    // [256] or null
   const float* add;     // [M,256] or null; out = add + A*W^T + bias  (may alias out)
   float* out;           // [M,256] fp32 or null
-  __half* out16;        // [M,256] fp16 or null
+  __half* out16;        // [M,256] fp16 or null: fp16(out_scale * value)
+  __half* out16_lo;     // [M,256] fp16 or null: fp16(out_scale * value - out16)  (hi/lo split)
+  float out_scale;      // applied to out16 / out16_lo only (0 = 1)
   int M;
 };
 int launch_linear_simt(dfm_ctx* ctx, const LinearArgs& a, cudaStream_t s);
@@ -175,10 +184,13 @@ struct EdgeArgs {
   float* agg;           // [B,N,256]
   __half* mstar;        // tc path, last layer
   float* fbuf;          // [B,L,4] out (last layer)
+  const __half* coord_img;   // weight image for launch_coord_tc (null = img_Wc1)
 };
 int launch_edge_simt(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
+int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, const __half* Alo,
+                   cudaStream_t s);
 
 int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s);
 int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,

@@ -1,0 +1,398 @@
+// Warp-specialised tcgen05 edge kernel (throughput path of the fused edge MLP):
+//   m = SiLU(W2 SiLU(u) + b2), gate, per-residue segment sum              (src/models/egnn.py:95-116, 139-148)
+//   u = A_i + B_j + radial * w1r + T[d, relpos] + T[omega, theta, phi]     (SURVEY App. A.5 / A.7 decomposition)
+//
+// One persistent CTA per SM, 17 warps:
+//   warps 0-7   producers: gather B_j / table rows (fp16, L2), form u/2 in packed half2, SiLU via tanh.approx.f16x2,
+//               write the 128 x 256 fp16 operand tile S into shared memory one 64-column K block at a time
+//   warp  16    MMA issuer: D[128 x 256] (TMEM, fp32) = S * (W2/2)^T, one tcgen05.commit per K block (frees that
+//               block for the next tile's build) and one per tile (accumulator ready)
+//   warps 8-15  epilogue: TMEM -> registers, + b2/2, SiLU in half2, gate logit, gate, 32-row column sums by
+//               shuffle transposition, segment sum of the two residues of the tile -> agg (fp32)
+// The fp16 weight image (128 KB) stays resident in shared memory; accumulators are double buffered in TMEM
+// (2 x 256 columns) so that build(t+1), MMA(t) and epilogue(t-1) overlap.
+//
+// All operands are pre-halved at production (A, B, tables, w1r, W2, b2 carry a factor 1/2), because
+// SiLU(x) = h + h * tanh(h) with h = x/2: one MUFU and one HFMA2 per element pair.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace ews {
+
+constexpr int TILE_M = 128;
+constexpr uint32_t W_BYTES = 256 * 256 * 2;          // 131072
+constexpr uint32_t S_BYTES = TILE_M * 256 * 2;       // 65536
+constexpr uint32_t W_KBLK = 256 * 128;               // bytes per 64-wide K block of the weight image
+constexpr uint32_t S_KBLK = TILE_M * 128;
+constexpr uint32_t OFF_W = 0;
+constexpr uint32_t OFF_S = W_BYTES;
+constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // b2/2 [256] half, wa [256] half, w1r' [256] half, (spare 512 B)
+constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [2 column halves][128 rows] float gate partials
+constexpr uint32_t OFF_AGG = OFF_PART + 2 * 128 * 4; // [4 lane quarters][256] float column sums
+constexpr uint32_t OFF_BAR = OFF_AGG + 4 * 256 * 4;  // 12 mbarriers + tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
+
+constexpr int NPROD = 8;                 // producer warps
+constexpr int NEPI = 8;                  // epilogue warps
+constexpr int NT = (NPROD + NEPI + 1) * 32;   // 544
+
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();   // a lost arrival must fail loudly, never hang the GPU
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- packed half2 helpers on raw 32-bit registers ---------------------------------------------------
+__device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b) {
+  uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t h2mul(uint32_t a, uint32_t b) {
+  uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t h2tanh(uint32_t a) {
+  uint32_t d; asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d;
+}
+// (lo, hi) fp32 -> packed f16x2, round to nearest, saturating to the finite range
+__device__ __forceinline__ uint32_t f2h2(float lo, float hi) {
+  uint32_t d; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
+}
+__device__ __forceinline__ float2 h2f2(uint32_t a) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&a));
+}
+// SiLU(2h) = h + h * tanh(h)
+__device__ __forceinline__ uint32_t h2silu(uint32_t h) { return h2fma(h, h2tanh(h), h); }
+
+struct Params {
+  int ntiles;
+  int total_nodes;          // B * N
+  int N, R, K;
+  int last;                 // spill gated messages of ligand residues (coordinate head input)
+  const __half* Wimg;       // (W2 / 2) fp16 SW128 image
+  const int4* emeta;        // [B*N, 64] {global row of j, Tdrp row, Totp row or -1, radial bits}
+  const __half* Ahi;        // [B*N, 256] fp16((W1s h_i + b1)/2)
+  const __half* Alo;        // [B*N, 256] residual of the above
+  const __half* Bm;         // [B*N, 256] fp16((W1d h_j)/2)
+  const __half* Tdrp;       // pre-halved merged tables
+  const __half* Totp;
+  const float* w1r;         // [256] fp32 (unhalved)
+  const float* b2;          // [256]
+  const float* wa;          // [256]
+  const float* ba;          // [1]
+  float* agg;               // [B*N, 256] fp32 out
+  __half* mstar;            // [B*L, 64, 256] fp16 (m* x 2^-6), last layer only
+};
+
+constexpr float RAD_SCALE = 0.03125f;     // radial is carried as fp16(radial / 32); w1r' = 32 * w1r / 2
+constexpr float MSTAR_SCALE = 0.015625f;  // gated messages are carried x 2^-6 in fp16 (column sums stay < 65504)
+
+// 32 lanes x NR packed registers -> lane l ends with the lane-sums of registers 2l and 2l+1 in v[0], v[1]
+template <int NR>
+__device__ __forceinline__ void lane_transpose_sum_h2(uint32_t* v, int lane) {
+#pragma unroll
+  for (int o = 16, n = NR; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+    const int half = n >> 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const uint32_t send = up ? v[i] : v[i + half];
+      const uint32_t keep = up ? v[i + half] : v[i];
+      v[i] = h2add(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  __half* vb2 = reinterpret_cast<__half*>(smem + OFF_VEC);         // b2/2
+  __half* vwa = vb2 + 256;
+  __half* vwr = vb2 + 512;                                          // 16 * w1r
+  float* part = reinterpret_cast<float*>(smem + OFF_PART);
+  float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+  const uint32_t bar_full = sbase + OFF_BAR;            // [4]
+  const uint32_t bar_empty = sbase + OFF_BAR + 32;      // [4]
+  const uint32_t bar_accf = sbase + OFF_BAR + 64;       // [2]
+  const uint32_t bar_acce = sbase + OFF_BAR + 80;       // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup ------------------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wimg);
+    uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
+    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
+    if (tid < 256) {
+      vb2[tid] = __float2half_rn(0.5f * p.b2[tid]);
+      vwa[tid] = __float2half_rn(p.wa[tid]);
+      vwr[tid] = __float2half_rn(p.w1r[tid] * (0.5f / RAD_SCALE));
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == NPROD + NEPI) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NPROD) {
+    // =================================== PRODUCERS ===================================================
+    // rows of this lane: r_i = warp*16 + 4 i + (lane >> 3), i = 0..3 (all in residue `warp >> 2` of the tile);
+    // 16-byte chunk c8 = lane & 7 of each 128-byte K-block row.
+    const int c8 = lane & 7, rsub = lane >> 3;
+    const int r0 = warp * 16 + rsub;
+    int4 nxt[4];
+    {
+      const int tile = blockIdx.x;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 4 * i;
+        const int node = tile * 2 + (r >> 6);
+        nxt[i] = make_int4(0, 40 * 66 + 32, -1, 0);
+        if (tile < p.ntiles && node < p.total_nodes) nxt[i] = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
+      }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      int4 cur[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      {
+        const int ntile = tile + (int)gridDim.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 4 * i;
+          const int node = ntile * 2 + (r >> 6);
+          nxt[i] = make_int4(0, 40 * 66 + 32, -1, 0);
+          if (ntile < p.ntiles && node < p.total_nodes) nxt[i] = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
+        }
+      }
+      int node = tile * 2 + (warp >> 2);
+      if (node >= p.total_nodes) node = p.total_nodes - 1;   // odd tail: rows are masked in the epilogue
+      uint32_t rad2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float rs = fminf(__int_as_float(cur[i].w) * RAD_SCALE, 65000.f);
+        rad2[i] = f2h2(rs, rs);
+      }
+#pragma unroll 1
+      for (int kb = 0; kb < 4; ++kb) {
+        const int colh = kb * 64 + c8 * 8;                  // first of this lane's 8 columns
+        const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(p.Ahi + (size_t)node * H + colh));
+        const uint4 alo = __ldg(reinterpret_cast<const uint4*>(p.Alo + (size_t)node * H + colh));
+        uint4 hb[4], td[4], to[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hb[i] = __ldg(reinterpret_cast<const uint4*>(p.Bm + (size_t)cur[i].x * H + colh));
+          td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)cur[i].y * H + colh));
+          to[i] = make_uint4(0, 0, 0, 0);
+          if (cur[i].z >= 0) to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)cur[i].z * H + colh));
+        }
+        const uint4 wr = *reinterpret_cast<const uint4*>(vwr + colh);
+        if (it > 0) mbar_wait(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1));   // MMA of the previous tile has read this block
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 4 * i;
+          uint4 s;
+          {
+            uint32_t q;
+            q = h2fma(rad2[i], wr.x, h2add(td[i].x, to[i].x)); s.x = h2silu(h2add(h2add(h2add(ahi.x, hb[i].x), q), alo.x));
+            q = h2fma(rad2[i], wr.y, h2add(td[i].y, to[i].y)); s.y = h2silu(h2add(h2add(h2add(ahi.y, hb[i].y), q), alo.y));
+            q = h2fma(rad2[i], wr.z, h2add(td[i].z, to[i].z)); s.z = h2silu(h2add(h2add(h2add(ahi.z, hb[i].z), q), alo.z));
+            q = h2fma(rad2[i], wr.w, h2add(td[i].w, to[i].w)); s.w = h2silu(h2add(h2add(h2add(ahi.w, hb[i].w), q), alo.w));
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4)) = s;
+        }
+        fence_async_smem();
+        mbar_arrive(bar_full + 8 * kb);
+      }
+    }
+  } else if (warp == NPROD + NEPI) {
+    // =================================== MMA ISSUER ===================================================
+    if (lane == 0) {
+      const uint64_t dW = make_desc(sbase + OFF_W);
+      const uint64_t dS = make_desc(sbase + OFF_S);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));   // epilogue drained this buffer
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar_full + 8 * kb, (uint32_t)(it & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t da = dS + (uint64_t)((kb * S_KBLK + k4 * 32) >> 4);
+            const uint64_t db = dW + (uint64_t)((kb * W_KBLK + k4 * 32) >> 4);
+            mma_f16(d_tmem, da, db, (kb | k4) ? 1u : 0u);
+          }
+          mma_commit(bar_empty + 8 * kb);
+        }
+        mma_commit(bar_accf + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== EPILOGUE =====================================================
+    const int e = warp - NPROD;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
+    const int ch = e >> 2;             // column half
+    const int erow = q * 32 + lane;
+    const int et = tid - NPROD * 32;   // 0..255
+    const float ba = p.ba[0];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int node = tile * 2 + (erow >> 6), k = erow & 63;
+      const bool valid = node < p.total_nodes && k < p.K;
+      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
+      uint32_t m[64];
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32_issue(taddr + c * 32, acc);
+        tmem_ld_wait();
+        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 bb = *reinterpret_cast<const uint4*>(vb2 + ch * 128 + c * 32 + g * 8);
+          const uint4 ww = *reinterpret_cast<const uint4*>(vwa + ch * 128 + c * 32 + g * 8);
+          const uint32_t x0 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1])), bb.x));
+          const uint32_t x1 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3])), bb.y));
+          const uint32_t x2 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5])), bb.z));
+          const uint32_t x3 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7])), bb.w));
+          m[c * 16 + g * 4 + 0] = x0; m[c * 16 + g * 4 + 1] = x1; m[c * 16 + g * 4 + 2] = x2; m[c * 16 + g * 4 + 3] = x3;
+          d0 = h2fma(x0, ww.x, d0); d1 = h2fma(x1, ww.y, d1); d2 = h2fma(x2, ww.z, d2); d3 = h2fma(x3, ww.w, d3);
+        }
+        const float2 f0 = h2f2(d0), f1 = h2f2(d1), f2 = h2f2(d2), f3 = h2f2(d3);
+        dot += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
+      part[ch * 128 + erow] = dot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float tot = part[erow] + part[128 + erow] + ba;
+      const float g = valid ? MSTAR_SCALE * __fdividef(1.f, 1.f + __expf(-tot)) : 0.f;
+      const uint32_t g2 = f2h2(g, g);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) m[i] = h2mul(m[i], g2);
+      if (p.last && valid) {
+        const int b = node / p.N, i = node - b * p.N;
+        if (i >= p.R) {
+          uint4* dst = reinterpret_cast<uint4*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + k) * H + ch * 128);
+#pragma unroll
+          for (int v4 = 0; v4 < 16; ++v4) dst[v4] = make_uint4(m[v4 * 4], m[v4 * 4 + 1], m[v4 * 4 + 2], m[v4 * 4 + 3]);
+        }
+      }
+      lane_transpose_sum_h2<64>(m, lane);       // lane l: columns ch*128 + 4l .. 4l+3 summed over this warp's 32 rows
+      {
+        const float2 s0 = h2f2(m[0]), s1 = h2f2(m[1]);
+        *reinterpret_cast<float4*>(aggp + q * 256 + ch * 128 + lane * 4) = make_float4(s0.x, s0.y, s1.x, s1.y);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const int hn = et >> 7, c2 = (et & 127) * 2;
+        const int nd = tile * 2 + hn;
+        if (nd < p.total_nodes) {
+          const float2 a0 = *reinterpret_cast<const float2*>(aggp + (2 * hn) * 256 + c2);
+          const float2 a1 = *reinterpret_cast<const float2*>(aggp + (2 * hn + 1) * 256 + c2);
+          *reinterpret_cast<float2*>(p.agg + (size_t)nd * H + c2) =
+              make_float2((a0.x + a1.x) * (1.f / MSTAR_SCALE), (a0.y + a1.y) * (1.f / MSTAR_SCALE));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPROD + NEPI) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+}  // namespace ews
+
+int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, const __half* Alo,
+                   cudaStream_t s) {
+  const LayerW& w = ctx->layer[a.layer];
+  ews::Params p{};
+  p.total_nodes = a.B * a.N;
+  p.ntiles = (p.total_nodes + 1) / 2;
+  p.N = a.N; p.R = a.R; p.K = a.K;
+  p.last = a.last ? 1 : 0;
+  p.Wimg = w.img_W2h;
+  p.emeta = emeta;
+  p.Ahi = Ahi; p.Alo = Alo;
+  p.Bm = reinterpret_cast<const __half*>(a.Bm);
+  p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
+  p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
+  p.agg = a.agg; p.mstar = a.mstar;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
+    attr = true;
+  }
+  const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
+  if (grid <= 0) return 0;
+  ews::k_edge_ws<<<grid, ews::NT, ews::SMEM_ALLOC, s>>>(p);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}

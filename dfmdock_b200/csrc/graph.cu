@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ pos, const float* __restrict__ cb,
         const int32_t* __restrict__ edges_in, const float* __restrict__ exp_noise, uint64_t seed,
         uint64_t stream_base, uint32_t fwd, int32_t* __restrict__ nbr, uint32_t* __restrict__ feat,
-        float* __restrict__ radial) {
+        float* __restrict__ radial, int4* __restrict__ emeta) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npad = (N + 31) & ~31;
@@ -253,6 +253,12 @@ k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ p
     nbr[o] = j;
     feat[o] = ft;
     radial[o] = r2;
+    {  // gather indices for the warp-specialised edge kernel (same decode as tc.cu k_tc<EDGE>)
+      const uint32_t otp = (ft >> 6) & 0x3FFFu;
+      const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
+      const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
+      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, __float_as_int(r2));
+    }
   }
 }
 
@@ -275,7 +281,7 @@ int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noi
   const int grid = (int)((rows + WARPS - 1) / WARPS);
   k_graph<WARPS><<<grid, WARPS * 32, smem, s>>>(B, N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, edges,
                                                 exp_noise, seed, stream_base, fwd_index, ws.nbr, ws.feat,
-                                                ws.radial);
+                                                ws.radial, ws.emeta);
   LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -35,18 +35,21 @@ __global__ void k_pair_table(const float* __restrict__ W1, const float* __restri
 // Merged gather tables for the tensor-core edge kernel: one row per (dist bin, relpos bin) pair -- with the three
 // zero-angle rows folded in for pairs whose angle bins are all 0 (masked: dist >= 22 A or self) -- and one row per
 // (omega, theta, phi) bin triple.  Sums are formed in fp32 and rounded to fp16 once.
-__global__ void k_merge_tables(const float* __restrict__ T32, __half* __restrict__ Tdrp, __half* __restrict__ Totp) {
+__global__ void k_merge_tables(const float* __restrict__ T32, __half* __restrict__ Tdrp, __half* __restrict__ Totp,
+                               __half* __restrict__ Tdrph, __half* __restrict__ Totph) {
   const int row = blockIdx.x, c = threadIdx.x;
   if (row < 2 * 40 * 66) {
     const int z = row / (40 * 66), d = (row / 66) % 40, rp = row % 66;
     float v = T32[(size_t)d * H + c] + T32[(size_t)(NSPATIAL + rp) * H + c];
     if (z) v += T32[(size_t)40 * H + c] + T32[(size_t)64 * H + c] + T32[(size_t)88 * H + c];
     Tdrp[(size_t)row * H + c] = __float2half_rn(v);
+    Tdrph[(size_t)row * H + c] = __float2half_rn(0.5f * v);
   } else {
     const int q = row - 2 * 40 * 66;
     const int o = q / (24 * 12), t = (q / 12) % 24, ph = q % 12;
     const float v = T32[(size_t)(40 + o) * H + c] + T32[(size_t)(64 + t) * H + c] + T32[(size_t)(88 + ph) * H + c];
     Totp[(size_t)q * H + c] = __float2half_rn(v);
+    Totph[(size_t)q * H + c] = __float2half_rn(0.5f * v);
   }
 }
 int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s) {
@@ -54,7 +57,7 @@ int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s) {
   k_pair_table<<<NSPATIAL + ctx->P, 256, 0, s>>>(w.W1, ctx->w["spatial_embed.weight"].d,
                                                 ctx->w["positional_embed.weight"].d, ctx->P, w.T32, w.T16, w.w1r);
   LAUNCH_CHECK(ctx);
-  k_merge_tables<<<2 * 40 * 66 + 24 * 24 * 12, 256, 0, s>>>(w.T32, w.Tdrp16, w.Totp16);
+  k_merge_tables<<<2 * 40 * 66 + 24 * 24 * 12, 256, 0, s>>>(w.T32, w.Tdrp16, w.Totp16, w.Tdrp16h, w.Totp16h);
   LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -389,12 +389,24 @@ __global__ void __launch_bounds__(NT, 1) k_tc(const Params p) {
             *reinterpret_cast<float4*>(p.lin.out + o + e4 * 4) = make_float4(m[e4 * 4], m[e4 * 4 + 1], m[e4 * 4 + 2], m[e4 * 4 + 3]);
         }
         if (p.lin.out16) {
+          const float osc = p.lin.out_scale != 0.f ? p.lin.out_scale : 1.f;
 #pragma unroll
           for (int e8 = 0; e8 < CW / 8; ++e8) {
             float x8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x8[e] = m[e8 * 8 + e];
-            *reinterpret_cast<uint4*>(p.lin.out16 + o + e8 * 8) = pack8(x8);
+            for (int e = 0; e < 8; ++e) x8[e] = m[e8 * 8 + e] * osc;
+            const uint4 hi = pack8(x8);
+            *reinterpret_cast<uint4*>(p.lin.out16 + o + e8 * 8) = hi;
+            if (p.lin.out16_lo) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&hi);
+#pragma unroll
+              for (int q2 = 0; q2 < 4; ++q2) {
+                const float2 f = __half22float2(hp[q2]);
+                x8[2 * q2] -= f.x;
+                x8[2 * q2 + 1] -= f.y;
+              }
+              *reinterpret_cast<uint4*>(p.lin.out16_lo + o + e8 * 8) = pack8(x8);
+            }
           }
         }
       }
@@ -573,7 +585,7 @@ int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   tc::Params p{};
   p.mode = tc::COORD;
   p.ntiles = (a.B * (a.N - a.R) + 1) / 2;
-  p.Wimg = w.img_Wc1;
+  p.Wimg = a.coord_img ? a.coord_img : w.img_Wc1;
   p.ed = a;
   p.v0 = w.bc1;
   p.v1 = w.wc2;
