@@ -31,6 +31,7 @@ def build_library(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dfmdock_b200.h")]
     nvcc = _nvcc()
+    extra = os.environ.get("DFM_NVCC_EXTRA", "").split()      # experiment switches, e.g. -DEWS_USE_ALO=0
     objs = []
     procs = []
     for src in SOURCES:
@@ -38,7 +39,7 @@ def build_library(force=False, verbose=False):
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
