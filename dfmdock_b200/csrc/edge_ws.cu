@@ -31,8 +31,9 @@ constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // b2/2 [256] half, wa [256
 constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [4 column quarters][128 rows] float gate partials
 constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [2 tile parities][4 lane quarters][256] float column sums
 constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [8 producer warps][2 slots][16 rows] int4 edge metadata
-constexpr uint32_t OFF_BAR = OFF_META + 8 * 2 * 16 * 16;  // 12 mbarriers + tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+constexpr uint32_t OFF_JRING = OFF_META + 8 * 2 * 16 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
+constexpr uint32_t OFF_BAR = OFF_JRING + 2 * 2 * 128 * 4;  // 16 mbarriers + tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 160;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
 
 constexpr int NPROD = 8;                 // producer warps
@@ -40,9 +41,9 @@ constexpr int NEPI = 16;                 // epilogue warps
 // 28 warps: 8 producers, 16 epilogue, 1 MMA issuer + 3 idle warps that only complete its warpgroup (setmaxnreg is a
 // warpgroup-wide operation: a lone 17th warp never finishes it and the epilogue's .inc then blocks forever).
 constexpr int NT = (NPROD + NEPI + 4) * 32;   // 896 -> 72 registers/thread at launch, pool 28*32*72 = 64512
-constexpr int PROD_REGS = 104;           // setmaxnreg: 8*32*104 + 16*32*64 + 4*32*24 = 62464 <= 64512
+constexpr int PROD_REGS = 104;           // setmaxnreg: 8*32*104 + 16*32*64 + 4*32*40 = 64512 <= 64512
 constexpr int EPI_REGS = 64;
-constexpr int MMA_REGS = 24;
+constexpr int MMA_REGS = 40;
 #ifndef EWS_USE_ALO
 #define EWS_USE_ALO 0     // carry A_i as fp16 hi + lo (1) or a single fp16 (0)
 #endif
@@ -61,23 +62,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint64_t gtimer() {
-  uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
-}
+// try_wait parks the thread inside the instruction for a hardware-bounded time; between retries back off so that
+// waiting warps do not eat the issue slots of the working warps.  A lost arrival traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  uint64_t t0 = 0;
-  do {
-    // the suspend-time hint parks the warp inside try_wait instead of spinning through the issue slots
+  uint32_t ok, tries = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  while (!ok) {
+    __nanosleep(40);
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-    if (!ok) {   // a lost arrival must fail loudly, never hang the GPU
-      const uint64_t t = gtimer();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ull) __trap();
-    }
-  } while (!ok);
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (++tries > (1u << 24)) __trap();
+  }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -111,6 +109,20 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- shared-memory accessors on 32-bit shared-space addresses (LDS/STS instead of generic LD/ST) ----------
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float ldsf(uint32_t a) { return __uint_as_float(lds32(a)); }
+__device__ __forceinline__ void stsf(uint32_t a, float v) { sts32(a, __float_as_uint(v)); }
 
 // ---- packed half2 helpers on raw 32-bit registers ---------------------------------------------------
 __device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b) {
@@ -181,9 +193,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   __half* vb2 = reinterpret_cast<__half*>(smem + OFF_VEC);         // b2/2
   __half* vwa = vb2 + 256;
   __half* vwr = vb2 + 512;                                          // 16 * w1r
-  float* part = reinterpret_cast<float*>(smem + OFF_PART);
-  float* aggp = reinterpret_cast<float*>(smem + OFF_AGG);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 144);
+  const uint32_t bar_bfull = sbase + OFF_BAR + 96;      // [4] B_j rows of a K block have landed in the S tile
   const uint32_t bar_full = sbase + OFF_BAR;            // [4]
   const uint32_t bar_empty = sbase + OFF_BAR + 32;      // [4]
   const uint32_t bar_accf = sbase + OFF_BAR + 64;       // [2]
@@ -204,6 +215,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NPROD + NEPI) {
@@ -224,34 +236,43 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
     const int c8 = lane & 7, rsub = lane >> 3;
     const int r0 = warp * 16 + rsub;
-    int4* mring = reinterpret_cast<int4*>(smem + OFF_META) + warp * 32;   // [2 slots][16 rows] private to this warp
     const int4 pad_meta = make_int4(0, 40 * 66 + 32, -1, 0);
-    struct GBuf { uint4 hb[2], td[2], to[2]; uint32_t rad[2]; };
-    auto issue = [&](GBuf& g, const int4* mslot, int kb, int beta) {
-      const int colh = kb * 64 + c8 * 8;
+    // B_j is already in the S tile (loader warps, cp.async); this role gathers the two table rows of each edge into
+    // registers one K block ahead (two buffers), forms u/2, applies SiLU and overwrites the 16-byte chunk in place.
+    struct GBuf { uint4 td[4], to[4]; uint4 a; };
+    const uint32_t mring_s = sbase + OFF_META + (uint32_t)warp * 512u;      // shared-space address of this warp's ring
+    const uint32_t vwr_s = sbase + OFF_VEC + 1024u + (uint32_t)c8 * 16u;
+    // swizzled byte offset of this lane's chunk in row r0 + 4 i of a K block: (r0 + 4 i) * 128 + ((c8 ^ (r & 7)) << 4)
+    uint32_t soff[4];
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int4 mt = mslot[4 * (2 * beta + s2) + rsub];
-        g.hb[s2] = __ldg(reinterpret_cast<const uint4*>(p.Bm + (size_t)mt.x * H + colh));
-        g.td[s2] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)mt.y * H + colh));
-        g.to[s2] = make_uint4(0, 0, 0, 0);
-        if (mt.z >= 0) g.to[s2] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)mt.z * H + colh));
-        const float rs = fminf(__int_as_float(mt.w) * RAD_SCALE, 65000.f);
-        g.rad[s2] = f2h2(rs, rs);
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 4 * i;
+      soff[i] = sbase + OFF_S + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+    }
+    auto issue = [&](GBuf& g, uint32_t mslot, size_t aoff, int kb) {
+      const int colh = kb * 64 + c8 * 8;
+      g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 mt = lds128(mslot + (uint32_t)(4 * i + rsub) * 16u);
+        g.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)mt.y * H + colh));
+        g.to[i] = make_uint4(0, 0, 0, 0);
+        if ((int)mt.z >= 0) g.to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)mt.z * H + colh));
       }
     };
-    auto compute = [&](const GBuf& g, const uint4& ahi, const uint4& alo, int kb, int beta) {
-      const uint4 wr = *reinterpret_cast<const uint4*>(vwr + kb * 64 + c8 * 8);
+    auto compute = [&](const GBuf& g, uint32_t mslot, int kb) {
+      const uint4 wr = lds128(vwr_s + (uint32_t)kb * 128u);
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int r = r0 + 4 * (2 * beta + s2);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t rad = lds32(mslot + (uint32_t)(4 * i + rsub) * 16u + 12u);
+        const uint32_t sa = soff[i] + (uint32_t)kb * S_KBLK;
+        const uint4 hb = lds128(sa);
         uint4 o;
-        uint32_t q;
-        q = h2fma(g.rad[s2], wr.x, h2add(g.td[s2].x, g.to[s2].x)); o.x = h2silu(EWS_USE_ALO ? h2add(h2add(h2add(ahi.x, g.hb[s2].x), q), alo.x) : h2add(h2add(ahi.x, g.hb[s2].x), q));
-        q = h2fma(g.rad[s2], wr.y, h2add(g.td[s2].y, g.to[s2].y)); o.y = h2silu(EWS_USE_ALO ? h2add(h2add(h2add(ahi.y, g.hb[s2].y), q), alo.y) : h2add(h2add(ahi.y, g.hb[s2].y), q));
-        q = h2fma(g.rad[s2], wr.z, h2add(g.td[s2].z, g.to[s2].z)); o.z = h2silu(EWS_USE_ALO ? h2add(h2add(h2add(ahi.z, g.hb[s2].z), q), alo.z) : h2add(h2add(ahi.z, g.hb[s2].z), q));
-        q = h2fma(g.rad[s2], wr.w, h2add(g.td[s2].w, g.to[s2].w)); o.w = h2silu(EWS_USE_ALO ? h2add(h2add(h2add(ahi.w, g.hb[s2].w), q), alo.w) : h2add(h2add(ahi.w, g.hb[s2].w), q));
-        *reinterpret_cast<uint4*>(smem + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4)) = o;
+        o.x = h2silu(h2add(h2add(g.a.x, hb.x), h2fma(rad, wr.x, h2add(g.td[i].x, g.to[i].x))));
+        o.y = h2silu(h2add(h2add(g.a.y, hb.y), h2fma(rad, wr.y, h2add(g.td[i].y, g.to[i].y))));
+        o.z = h2silu(h2add(h2add(g.a.z, hb.z), h2fma(rad, wr.z, h2add(g.td[i].z, g.to[i].z))));
+        o.w = h2silu(h2add(h2add(g.a.w, hb.w), h2fma(rad, wr.w, h2add(g.td[i].w, g.to[i].w))));
+        sts128(sa, o);
       }
     };
     auto load_meta = [&](int tile) -> int4 {     // lanes 0..15: edge metadata of row warp*16 + lane of `tile`
@@ -267,72 +288,117 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       return (size_t)node * H + c8 * 8;
     };
     GBuf g0, g1;
-    uint4 ahi, alo = make_uint4(0, 0, 0, 0), ahn, aln = make_uint4(0, 0, 0, 0);
+    const int4 pad_rad0 = pad_meta;
+    (void)pad_rad0;
     if ((int)blockIdx.x < p.ntiles) {
       const int4 m0 = load_meta(blockIdx.x);
-      if (lane < 16) mring[lane] = m0;
+      if (lane < 16) sts128(mring_s + (uint32_t)lane * 16u, make_uint4(m0.x, m0.y, m0.z, m0.w));
       __syncwarp();
-      issue(g0, mring, 0, 0);
-      const size_t ao = a_node(blockIdx.x);
-      ahi = __ldg(reinterpret_cast<const uint4*>(p.Ahi + ao));
-      if (EWS_USE_ALO) alo = __ldg(reinterpret_cast<const uint4*>(p.Alo + ao));
+      issue(g0, mring_s, a_node(blockIdx.x), 0);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int4* mcur = mring + (it & 1) * 16;
-      int4* mnext = mring + ((it & 1) ^ 1) * 16;
+      const uint32_t mcur = mring_s + (uint32_t)(it & 1) * 256u;
+      const uint32_t mnext = mring_s + (uint32_t)((it & 1) ^ 1) * 256u;
       const int ntile = tile + (int)gridDim.x;
       const bool has_next = ntile < p.ntiles;
       const int4 nm = load_meta(ntile);
       const size_t ao = a_node(tile), aon = a_node(has_next ? ntile : tile);
-#pragma unroll 1
-      for (int kb = 0; kb < 4; ++kb) {
-        issue(g1, mcur, kb, 1);
-        if (it > 0) mbar_wait(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1));   // MMA of the previous tile has read this block
-        compute(g0, ahi, alo, kb, 0);
-        if (kb == 1) {
-          if (lane < 16) mnext[lane] = nm;
-          __syncwarp();
-        }
-        if (kb < 3) {
-          issue(g0, mcur, kb + 1, 0);
-          ahn = __ldg(reinterpret_cast<const uint4*>(p.Ahi + ao + (kb + 1) * 64));
-          if (EWS_USE_ALO) aln = __ldg(reinterpret_cast<const uint4*>(p.Alo + ao + (kb + 1) * 64));
-        } else if (has_next) {
-          issue(g0, mnext, 0, 0);
-          ahn = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aon));
-          if (EWS_USE_ALO) aln = __ldg(reinterpret_cast<const uint4*>(p.Alo + aon));
-        }
-        compute(g1, ahi, alo, kb, 1);
-        fence_async_smem();
-        mbar_arrive(bar_full + 8 * kb);
-        ahi = ahn; alo = aln;
-      }
+      const uint32_t par = (uint32_t)(it & 1);
+      // kb 0 (buffer 0); prefetch kb 1
+      issue(g1, mcur, ao, 1);
+      mbar_wait(bar_bfull + 0, par);
+      compute(g0, mcur, 0);
+      fence_async_smem(); mbar_arrive(bar_full + 0);
+      // kb 1 (buffer 1); prefetch kb 2
+      issue(g0, mcur, ao, 2);
+      mbar_wait(bar_bfull + 8, par);
+      compute(g1, mcur, 1);
+      fence_async_smem(); mbar_arrive(bar_full + 8);
+      if (lane < 16) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
+      __syncwarp();
+      // kb 2 (buffer 0); prefetch kb 3
+      issue(g1, mcur, ao, 3);
+      mbar_wait(bar_bfull + 16, par);
+      compute(g0, mcur, 2);
+      fence_async_smem(); mbar_arrive(bar_full + 16);
+      // kb 3 (buffer 1); prefetch kb 0 of the next tile
+      if (has_next) issue(g0, mnext, aon, 0);
+      mbar_wait(bar_bfull + 24, par);
+      compute(g1, mcur, 3);
+      fence_async_smem(); mbar_arrive(bar_full + 24);
     }
   } else if (warp >= NPROD + NEPI) {
-    // =================================== MMA ISSUER ===================================================
+    // =================================== MMA ISSUER + B_j LOADERS ======================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
-    if (warp == NPROD + NEPI && lane == 0) {
-      const uint64_t dW = make_desc(sbase + OFF_W);
-      const uint64_t dS = make_desc(sbase + OFF_S);
+    if (warp == NPROD + NEPI) {
+      if (lane == 0) {
+        const uint64_t dW = make_desc(sbase + OFF_W);
+        const uint64_t dS = make_desc(sbase + OFF_S);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+          const int buf = it & 1;
+          if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));   // epilogue drained this buffer
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(bar_full + 8 * kb, (uint32_t)(it & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t da = dS + (uint64_t)((kb * S_KBLK + k4 * 32) >> 4);
+              const uint64_t db = dW + (uint64_t)((kb * W_KBLK + k4 * 32) >> 4);
+              mma_f16(d_tmem, da, db, (kb | k4) ? 1u : 0u);
+            }
+            mma_commit(bar_empty + 8 * kb);
+          }
+          mma_commit(bar_accf + 8 * buf);
+        }
+      }
+    } else if (warp <= NPROD + NEPI + 2) {
+      // Loader warp lw (0/1) copies the B_j rows of K blocks lw and lw+2 of every tile straight into the S tile with
+      // cp.async (16 bytes per lane and instruction, no registers held while in flight); the producers add the rest
+      // in place.  A block may be refilled as soon as the MMA of the previous tile has consumed it (bar_empty).
+      const int lw = warp - (NPROD + NEPI + 1);
+      const uint32_t jring_s = sbase + OFF_JRING + (uint32_t)lw * 1024u;
+      const int c8 = lane & 7, rsub = lane >> 3;
+      auto load_j = [&](int tile, int i) -> int {        // global row of the neighbour of tile row lane + 32 i
+        const int r = lane + 32 * i;
+        const int node = tile * 2 + (r >> 6);
+        int j = 0;
+        if (tile < p.ntiles && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
+        return j;
+      };
+      if ((int)blockIdx.x < p.ntiles) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts32(jring_s + (uint32_t)(lane + 32 * i) * 4u, (uint32_t)load_j(blockIdx.x, i));
+      }
+      __syncwarp();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));   // epilogue drained this buffer
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-#pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(bar_full + 8 * kb, (uint32_t)(it & 1));
-          tc_fence_after();
+        const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u;
+        int jn[4];
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t da = dS + (uint64_t)((kb * S_KBLK + k4 * 32) >> 4);
-            const uint64_t db = dW + (uint64_t)((kb * W_KBLK + k4 * 32) >> 4);
-            mma_f16(d_tmem, da, db, (kb | k4) ? 1u : 0u);
+        for (int i = 0; i < 4; ++i) jn[i] = load_j(tile + (int)gridDim.x, i);
+#pragma unroll 1
+        for (int kk = 0; kk < 2; ++kk) {
+          const int kb = lw + 2 * kk;
+          if (it > 0) mbar_wait(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1));
+          const __half* src0 = p.Bm + kb * 64 + c8 * 8;
+          const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int r = rsub + 4 * i;
+            const __half* src = src0 + (size_t)lds32(jc + (uint32_t)r * 4u) * H;
+            const uint32_t dst = dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
           }
-          mma_commit(bar_empty + 8 * kb);
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_bfull + 8 * kb) : "memory");
         }
-        mma_commit(bar_accf + 8 * buf);
+        const uint32_t jnx = jring_s + (uint32_t)((it & 1) ^ 1) * 512u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts32(jnx + (uint32_t)(lane + 32 * i) * 4u, (uint32_t)jn[i]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -347,6 +413,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     const int hn = q >> 1;             // residue of the tile this warp's rows belong to
     const int ecol = (cq * 2 + (q & 1)) * 32 + lane;   // column this thread writes in the final combine (0..255)
     const float ba = p.ba[0];
+    const uint32_t vec_s = sbase + OFF_VEC + (uint32_t)cq * 128u;
+    const uint32_t part_s = sbase + OFF_PART + (uint32_t)erow * 4u;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -365,8 +433,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint4 bb = *reinterpret_cast<const uint4*>(vb2 + cq * 64 + c * 16 + g * 8);
-          const uint4 ww = *reinterpret_cast<const uint4*>(vwa + cq * 64 + c * 16 + g * 8);
+          const uint4 bb = lds128(vec_s + (uint32_t)(c * 16 + g * 8) * 2u);
+          const uint4 ww = lds128(vec_s + 512u + (uint32_t)(c * 16 + g * 8) * 2u);
           const uint32_t x0 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1])), bb.x));
           const uint32_t x1 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3])), bb.y));
           const uint32_t x2 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5])), bb.z));
@@ -379,9 +447,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
-      part[cq * 128 + erow] = dot;
+      stsf(part_s + (uint32_t)cq * 512u, dot);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the 4 column quarters of this row quarter
-      const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]) + ba;
+      const float tot = (ldsf(part_s) + ldsf(part_s + 512u)) + (ldsf(part_s + 1024u) + ldsf(part_s + 1536u)) + ba;
       const float g = valid ? MSTAR_SCALE * __fdividef(1.f, 1.f + __expf(-tot)) : 0.f;
       const uint32_t g2 = f2h2(g, g);
 #pragma unroll
@@ -395,11 +463,15 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         }
       }
       lane_transpose_sum_h2<32>(m, lane);       // lane l: columns cq*64 + 2l, 2l+1 summed over this warp's 32 rows
-      float* ag = aggp + buf * 1024;
-      *reinterpret_cast<float2*>(ag + q * 256 + cq * 64 + lane * 2) = h2f2(m[0]);
+      const uint32_t ag = sbase + OFF_AGG + (uint32_t)buf * 4096u;
+      {
+        const float2 cs = h2f2(m[0]);
+        const uint32_t a0 = ag + (uint32_t)(q * 256 + cq * 64 + lane * 2) * 4u;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a0), "f"(cs.x), "f"(cs.y) : "memory");
+      }
       asm volatile("bar.sync %0, 256;" ::"r"(5 + hn) : "memory");     // the 8 warps that hold this residue's rows
       if (node < p.total_nodes)
-        p.agg[(size_t)node * H + ecol] = (ag[(2 * hn) * 256 + ecol] + ag[(2 * hn + 1) * 256 + ecol]) * (1.f / MSTAR_SCALE);
+        p.agg[(size_t)node * H + ecol] = (ldsf(ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u) + ldsf(ag + (uint32_t)((2 * hn + 1) * 256 + ecol) * 4u)) * (1.f / MSTAR_SCALE);
     }
   }
   tc_fence_before();

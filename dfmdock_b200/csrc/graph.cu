@@ -257,7 +257,9 @@ k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ p
       const uint32_t otp = (ft >> 6) & 0x3FFFu;
       const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
       const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
-      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, __float_as_int(r2));
+      // radial travels as packed half2 of radial / 32 (edge_ws.cu RAD_SCALE), clamped to the fp16 range
+      const __half2 rh = __float2half2_rn(fminf(r2 * 0.03125f, 65000.f));
+      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, *reinterpret_cast<const int*>(&rh));
     }
   }
 }
