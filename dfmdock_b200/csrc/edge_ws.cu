@@ -3,11 +3,11 @@
 //   u = A_i + B_j + radial * w1r + T[d, relpos] + T[omega, theta, phi]     (SURVEY App. A.5 / A.7 decomposition)
 //
 // One persistent CTA per SM, 28 warps (25 active):
-//   warps 0-7   producers: gather B_j / table rows (fp16, L2), form u/2 in packed half2, SiLU via tanh.approx.f16x2,
+//   warps 0-15  producers: gather B_j / table rows (fp16, L2), form u/2 in packed half2, SiLU via tanh.approx.f16x2,
 //               write the 128 x 256 fp16 operand tile S into shared memory one 64-column K block at a time
 //   warp  24    MMA issuer: D[128 x 256] (TMEM, fp32) = S * (W2/2)^T, one tcgen05.commit per K block (frees that
 //               block for the next tile's build) and one per tile (accumulator ready)
-//   warps 8-23  epilogue: TMEM -> registers, + b2/2, SiLU in half2, gate logit, gate, 32-row column sums by
+//   warps 16-23 epilogue: TMEM -> registers, + b2/2, SiLU in half2, gate logit, gate, 32-row column sums by
 //               shuffle transposition, segment sum of the two residues of the tile -> agg (fp32)
 // The fp16 weight image (128 KB) stays resident in shared memory; accumulators are double buffered in TMEM
 // (2 x 256 columns) so that build(t+1), MMA(t) and epilogue(t-1) overlap.
@@ -28,21 +28,21 @@ constexpr uint32_t S_KBLK = TILE_M * 128;
 constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_S = W_BYTES;
 constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // b2/2 [256] half, wa [256] half, w1r' [256] half, (spare 512 B)
-constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [4 column quarters][128 rows] float gate partials
+constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [<=4 column groups][128 rows] float gate partials
 constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [2 tile parities][4 lane quarters][256] float column sums
-constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [8 producer warps][2 slots][16 rows] int4 edge metadata
-constexpr uint32_t OFF_JRING = OFF_META + 8 * 2 * 16 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
+constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [16 producer warps][2 slots][8 rows] int4 edge metadata
+constexpr uint32_t OFF_JRING = OFF_META + 16 * 2 * 8 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
 constexpr uint32_t OFF_BAR = OFF_JRING + 2 * 2 * 128 * 4;  // 16 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 160;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
 
-constexpr int NPROD = 8;                 // producer warps
-constexpr int NEPI = 16;                 // epilogue warps
+constexpr int NPROD = 16;                // producer warps
+constexpr int NEPI = 8;                  // epilogue warps
 // 28 warps: 8 producers, 16 epilogue, 1 MMA issuer + 3 idle warps that only complete its warpgroup (setmaxnreg is a
 // warpgroup-wide operation: a lone 17th warp never finishes it and the epilogue's .inc then blocks forever).
 constexpr int NT = (NPROD + NEPI + 4) * 32;   // 896 -> 72 registers/thread at launch, pool 28*32*72 = 64512
-constexpr int PROD_REGS = 104;           // setmaxnreg: 8*32*104 + 16*32*64 + 4*32*40 = 64512 <= 64512
-constexpr int EPI_REGS = 64;
+constexpr int PROD_REGS = 64;            // setmaxnreg: 16*32*64 + 8*32*104 + 4*32*40 = 64512 <= 64512
+constexpr int EPI_REGS = 104;
 constexpr int MMA_REGS = 40;
 #ifndef EWS_USE_ALO
 #define EWS_USE_ALO 0     // carry A_i as fp16 hi + lo (1) or a single fp16 (0)
@@ -233,19 +233,19 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     // rows of this lane: r_i = warp*16 + 4 i + (lane >> 3), i = 0..3 (all in residue `warp >> 2` of the tile);
     // 16-byte chunk c8 = lane & 7 of each 128-byte K-block row.  Work item = (K block, pair of rows); the gathers of
     // item n+1 are in flight while item n is computed (two register buffers), across K blocks and across tiles.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
     const int c8 = lane & 7, rsub = lane >> 3;
-    const int r0 = warp * 16 + rsub;
+    const int r0 = warp * 8 + rsub;
     const int4 pad_meta = make_int4(0, 40 * 66 + 32, -1, 0);
     // B_j is already in the S tile (loader warps, cp.async); this role gathers the two table rows of each edge into
     // registers one K block ahead (two buffers), forms u/2, applies SiLU and overwrites the 16-byte chunk in place.
-    struct GBuf { uint4 td[4], to[4]; uint4 a; };
-    const uint32_t mring_s = sbase + OFF_META + (uint32_t)warp * 512u;      // shared-space address of this warp's ring
+    struct GBuf { uint4 td[2], to[2]; uint4 a; };
+    const uint32_t mring_s = sbase + OFF_META + (uint32_t)warp * 256u;      // shared-space address of this warp's ring
     const uint32_t vwr_s = sbase + OFF_VEC + 1024u + (uint32_t)c8 * 16u;
     // swizzled byte offset of this lane's chunk in row r0 + 4 i of a K block: (r0 + 4 i) * 128 + ((c8 ^ (r & 7)) << 4)
-    uint32_t soff[4];
+    uint32_t soff[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       const int r = r0 + 4 * i;
       soff[i] = sbase + OFF_S + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
     }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const int colh = kb * 64 + c8 * 8;
       g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const uint4 mt = lds128(mslot + (uint32_t)(4 * i + rsub) * 16u);
         g.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)mt.y * H + colh));
         g.to[i] = make_uint4(0, 0, 0, 0);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     auto compute = [&](const GBuf& g, uint32_t mslot, int kb) {
       const uint4 wr = lds128(vwr_s + (uint32_t)kb * 128u);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const uint32_t rad = lds32(mslot + (uint32_t)(4 * i + rsub) * 16u + 12u);
         const uint32_t sa = soff[i] + (uint32_t)kb * S_KBLK;
         const uint4 hb = lds128(sa);
@@ -275,15 +275,15 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         sts128(sa, o);
       }
     };
-    auto load_meta = [&](int tile) -> int4 {     // lanes 0..15: edge metadata of row warp*16 + lane of `tile`
+    auto load_meta = [&](int tile) -> int4 {     // lanes 0..7: edge metadata of row warp*8 + lane of `tile`
       int4 mt = pad_meta;
-      const int r = warp * 16 + (lane & 15);
+      const int r = warp * 8 + (lane & 7);
       const int node = tile * 2 + (r >> 6);
       if (tile < p.ntiles && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
       return mt;
     };
     auto a_node = [&](int tile) -> size_t {
-      int node = tile * 2 + (warp >> 2);
+      int node = tile * 2 + (warp >> 3);
       if (node >= p.total_nodes) node = p.total_nodes - 1;   // odd tail: those rows are masked in the epilogue
       return (size_t)node * H + c8 * 8;
     };
@@ -292,14 +292,14 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     (void)pad_rad0;
     if ((int)blockIdx.x < p.ntiles) {
       const int4 m0 = load_meta(blockIdx.x);
-      if (lane < 16) sts128(mring_s + (uint32_t)lane * 16u, make_uint4(m0.x, m0.y, m0.z, m0.w));
+      if (lane < 8) sts128(mring_s + (uint32_t)lane * 16u, make_uint4(m0.x, m0.y, m0.z, m0.w));
       __syncwarp();
       issue(g0, mring_s, a_node(blockIdx.x), 0);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t mcur = mring_s + (uint32_t)(it & 1) * 256u;
-      const uint32_t mnext = mring_s + (uint32_t)((it & 1) ^ 1) * 256u;
+      const uint32_t mcur = mring_s + (uint32_t)(it & 1) * 128u;
+      const uint32_t mnext = mring_s + (uint32_t)((it & 1) ^ 1) * 128u;
       const int ntile = tile + (int)gridDim.x;
       const bool has_next = ntile < p.ntiles;
       const int4 nm = load_meta(ntile);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       mbar_wait(bar_bfull + 8, par);
       compute(g1, mcur, 1);
       fence_async_smem(); mbar_arrive(bar_full + 8);
-      if (lane < 16) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
+      if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
       __syncwarp();
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       // cp.async (16 bytes per lane and instruction, no registers held while in flight); the producers add the rest
       // in place.  A block may be refilled as soon as the MMA of the previous tile has consumed it (bar_empty).
       const int lw = warp - (NPROD + NEPI + 1);
+      // j ring: [2 slots][4 row residues][32] -> the 32 rows (rsub + 4 i) of one lane are contiguous (8 x LDS.128)
       const uint32_t jring_s = sbase + OFF_JRING + (uint32_t)lw * 1024u;
       const int c8 = lane & 7, rsub = lane >> 3;
       auto load_j = [&](int tile, int i) -> int {        // global row of the neighbour of tile row lane + 32 i
@@ -369,14 +370,20 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         if (tile < p.ntiles && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
         return j;
       };
+      // row r = lane + 32 i sits at ring index (r & 3) * 32 + (r >> 2)
+      const uint32_t jput = (uint32_t)((lane & 3) * 32 + (lane >> 2)) * 4u;
       if ((int)blockIdx.x < p.ntiles) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jring_s + (uint32_t)(lane + 32 * i) * 4u, (uint32_t)load_j(blockIdx.x, i));
+        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(blockIdx.x, i));
       }
       __syncwarp();
+      // destination of this lane's chunk in row rsub + 4 i: (rsub + 4 i) * 128 + ((c8 ^ ((rsub + 4 i) & 7)) << 4);
+      // (rsub + 4 i) & 7 alternates between rsub and rsub + 4 -> two swizzled chunk offsets
+      const uint32_t dsw0 = (uint32_t)((c8 ^ rsub) << 4), dsw1 = (uint32_t)((c8 ^ (rsub + 4)) << 4);
+      const char* srcb = reinterpret_cast<const char*>(p.Bm) + c8 * 16;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u;
+        const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u + (uint32_t)rsub * 128u;
         int jn[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) jn[i] = load_j(tile + (int)gridDim.x, i);
@@ -384,36 +391,38 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = lw + 2 * kk;
           if (it > 0) mbar_wait(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1));
-          const __half* src0 = p.Bm + kb * 64 + c8 * 8;
-          const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int r = rsub + 4 * i;
-            const __half* src = src0 + (size_t)lds32(jc + (uint32_t)r * 4u) * H;
-            const uint32_t dst = dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          const char* src0 = srcb + kb * 128;
+          const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)rsub * 128u;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const uint4 j4 = lds128(jc + (uint32_t)i4 * 16u);
+            const uint32_t d = dst0 + (uint32_t)i4 * 2048u;      // rows rsub + 16 i4 + {0, 4, 8, 12}
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + dsw0), "l"(src0 + (size_t)j4.x * 512) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u + dsw1), "l"(src0 + (size_t)j4.y * 512) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1024u + dsw0), "l"(src0 + (size_t)j4.z * 512) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1536u + dsw1), "l"(src0 + (size_t)j4.w * 512) : "memory");
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_bfull + 8 * kb) : "memory");
         }
-        const uint32_t jnx = jring_s + (uint32_t)((it & 1) ^ 1) * 512u;
+        const uint32_t jnx = jring_s + (uint32_t)((it & 1) ^ 1) * 512u + jput;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jnx + (uint32_t)(lane + 32 * i) * 4u, (uint32_t)jn[i]);
+        for (int i = 0; i < 4; ++i) sts32(jnx + (uint32_t)i * 32u, (uint32_t)jn[i]);
         __syncwarp();
       }
     }
     __syncwarp();
   } else {
     // =================================== EPILOGUE =====================================================
-    // 16 warps = 4 TMEM lane quarters (rows) x 4 column quarters; warp (q, cq) owns rows q*32.. and columns cq*64..
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    // 8 warps = 4 TMEM lane quarters (rows) x 2 column halves; warp (q, ch) owns rows q*32.. and columns ch*128..
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int e = warp - NPROD;
     const int q = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
-    const int cq = e >> 2;             // column quarter
+    const int ch = e >> 2;             // column half
     const int erow = q * 32 + lane;
     const int hn = q >> 1;             // residue of the tile this warp's rows belong to
-    const int ecol = (cq * 2 + (q & 1)) * 32 + lane;   // column this thread writes in the final combine (0..255)
+    const int ecol = ((ch * 2 + (q & 1)) * 32 + lane) * 2;   // first of the 2 columns this thread writes in the final combine
     const float ba = p.ba[0];
-    const uint32_t vec_s = sbase + OFF_VEC + (uint32_t)cq * 128u;
+    const uint32_t vec_s = sbase + OFF_VEC + (uint32_t)ch * 256u;
     const uint32_t part_s = sbase + OFF_PART + (uint32_t)erow * 4u;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -422,11 +431,11 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const bool valid = node < p.total_nodes && k < p.K;
       mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cq * 64);
-      uint32_t m[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
+      uint32_t m[64];
       float dot = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 8; ++c) {
         uint32_t acc[16];
         tmem_ld16_issue(taddr + c * 16, acc);
         tmem_ld_wait();
@@ -447,31 +456,36 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
-      stsf(part_s + (uint32_t)cq * 512u, dot);
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the 4 column quarters of this row quarter
-      const float tot = (ldsf(part_s) + ldsf(part_s + 512u)) + (ldsf(part_s + 1024u) + ldsf(part_s + 1536u)) + ba;
+      stsf(part_s + (uint32_t)ch * 512u, dot);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the 2 column halves of this row quarter
+      const float tot = (ldsf(part_s) + ldsf(part_s + 512u)) + ba;
       const float g = valid ? MSTAR_SCALE * __fdividef(1.f, 1.f + __expf(-tot)) : 0.f;
       const uint32_t g2 = f2h2(g, g);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) m[i] = h2mul(m[i], g2);
+      for (int i = 0; i < 64; ++i) m[i] = h2mul(m[i], g2);
       if (p.last && valid) {
         const int b = node / p.N, i = node - b * p.N;
         if (i >= p.R) {
-          uint4* dst = reinterpret_cast<uint4*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + k) * H + cq * 64);
+          uint4* dst = reinterpret_cast<uint4*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + k) * H + ch * 128);
 #pragma unroll
-          for (int v4 = 0; v4 < 8; ++v4) dst[v4] = make_uint4(m[v4 * 4], m[v4 * 4 + 1], m[v4 * 4 + 2], m[v4 * 4 + 3]);
+          for (int v4 = 0; v4 < 16; ++v4) dst[v4] = make_uint4(m[v4 * 4], m[v4 * 4 + 1], m[v4 * 4 + 2], m[v4 * 4 + 3]);
         }
       }
-      lane_transpose_sum_h2<32>(m, lane);       // lane l: columns cq*64 + 2l, 2l+1 summed over this warp's 32 rows
+      lane_transpose_sum_h2<64>(m, lane);       // lane l: columns ch*128 + 4l .. 4l+3 summed over this warp's 32 rows
       const uint32_t ag = sbase + OFF_AGG + (uint32_t)buf * 4096u;
       {
-        const float2 cs = h2f2(m[0]);
-        const uint32_t a0 = ag + (uint32_t)(q * 256 + cq * 64 + lane * 2) * 4u;
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a0), "f"(cs.x), "f"(cs.y) : "memory");
+        const float2 s0 = h2f2(m[0]), s1 = h2f2(m[1]);
+        const uint32_t a0 = ag + (uint32_t)(q * 256 + ch * 128 + lane * 4) * 4u;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(s0.x), "f"(s0.y), "f"(s1.x), "f"(s1.y) : "memory");
       }
-      asm volatile("bar.sync %0, 256;" ::"r"(5 + hn) : "memory");     // the 8 warps that hold this residue's rows
-      if (node < p.total_nodes)
-        p.agg[(size_t)node * H + ecol] = (ldsf(ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u) + ldsf(ag + (uint32_t)((2 * hn + 1) * 256 + ecol) * 4u)) * (1.f / MSTAR_SCALE);
+      asm volatile("bar.sync %0, 128;" ::"r"(5 + hn) : "memory");     // the 4 warps that hold this residue's rows
+      if (node < p.total_nodes) {
+        const uint32_t a0 = ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u;
+        float2 o;
+        o.x = (ldsf(a0) + ldsf(a0 + 1024u)) * (1.f / MSTAR_SCALE);
+        o.y = (ldsf(a0 + 4u) + ldsf(a0 + 1028u)) * (1.f / MSTAR_SCALE);
+        *reinterpret_cast<float2*>(p.agg + (size_t)node * H + ecol) = o;
+      }
     }
   }
   tc_fence_before();
