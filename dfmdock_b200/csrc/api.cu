@@ -54,6 +54,10 @@ Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base) {
   w.esum = (float*)take(b * R * 4 * 4);
   w.tsc = (float*)take(b * 8 * 4);
   w.emeta = (int4*)take(b * N * SLOTS * 16);
+  w.h16 = (__half*)take(b * N * H * 2);
+  w.agg16 = (__half*)take(b * N * H * 2);
+  w.gscale = (float*)take(b * H * 4);
+  w.gshift = (float*)take(b * H * 4);
   w.bytes = off;
   return w;
 }
@@ -304,10 +308,35 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
                                sizeof(int32_t) * ctx->K, (size_t)M, cudaMemcpyDeviceToDevice, s));
   }
   if ((rc = launch_broadcast_h0(ctx, B, ws, s))) return rc;
-  for (int l = 0; l < DFM_DEPTH; ++l) {
+  const bool fast = !fp32 && ctx->edge_kernel == 1;
+  for (int l = 0; fast && l < DFM_DEPTH; ++l) {
+    // throughput path: fp16 activations between kernels, warp-specialised edge kernel, fused node-side GEMMs
     const LayerW& w = ctx->layer[l];
     const bool last = l == DFM_DEPTH - 1;
-    const bool ews = !fp32 && ctx->edge_kernel == 1;
+    __half* Ah = reinterpret_cast<__half*>(ws.A);
+    __half* Bm = reinterpret_cast<__half*>(ws.Bm);
+    if ((rc = launch_node_ab(ctx, l, M, ws.h16, Ah, Bm, s))) return rc;
+    EdgeArgs ea{};
+    ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
+    ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
+    ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf; ea.coord_img = w.img_Wc1s;
+    const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
+    if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
+    if ((rc = launch_edge_ws(ctx, ea, ws.emeta, Ah, ws.agg16, s))) return rc;
+    if (prof) {
+      CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], s));
+      ctx->prof_used += 2;
+    }
+    if (last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
+    if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
+    if ((rc = launch_node_z(ctx, l, M, ws.h16, ws.agg16, ws.z, s))) return rc;
+    if ((rc = launch_graphnorm_stats(ctx, B, l, ws.z, ws.gscale, ws.gshift, s))) return rc;
+    if ((rc = launch_node_h(ctx, l, M, ws.z, ws.gscale, ws.gshift, ws.h, ws.h16, s))) return rc;
+  }
+  for (int l = 0; !fast && l < DFM_DEPTH; ++l) {
+    const LayerW& w = ctx->layer[l];
+    const bool last = l == DFM_DEPTH - 1;
+    const bool ews = false;
     __half* Ahi = reinterpret_cast<__half*>(ws.A);
     __half* Alo = Ahi + (size_t)M * H;
     LinearArgs la{};
@@ -331,8 +360,6 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     if (ews) ea.coord_img = w.img_Wc1s;
     if (fp32) {
       if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
-    } else if (ews) {
-      if ((rc = launch_edge_ws(ctx, ea, ws.emeta, Ahi, Alo, s))) return rc;
     } else {
       if ((rc = launch_edge_tc(ctx, ea, s))) return rc;
     }

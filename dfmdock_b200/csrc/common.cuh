@@ -146,7 +146,11 @@ struct Workspace {
   float* fbuf;       // [B,L,4]
   float* esum;       // [B,R,2]
   float* tsc;        // [B,8] tr_score(3) rot_score(3) scratch when the caller passes NULL
-  int4* emeta;       // [B,N,64] {global row of j, Tdrp row, Totp row or -1, radial bits} (edge_ws.cu)
+  int4* emeta;       // [B,N,64] {global row of j, Tdrp row, Totp row or -1, packed half2 radial/32} (edge_ws.cu)
+  __half* h16;       // [B,N,256] fp16 copy of h (operand of the node-side GEMMs, node_tc.cu)
+  __half* agg16;     // [B,N,256] fp16(agg * 2^-6) written by edge_ws.cu
+  float* gscale;     // [B,256] GraphNorm weight * rstd
+  float* gshift;     // [B,256] GraphNorm bias - mean*mean_scale*gscale
   size_t bytes;
 };
 
@@ -189,14 +193,18 @@ struct EdgeArgs {
 int launch_edge_simt(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_edge_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
-int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, const __half* Alo,
-                   cudaStream_t s);
+int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, __half* agg16, cudaStream_t s);
 
 int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s);
 int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
                  uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s);
 int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s);
+int launch_graphnorm_stats(dfm_ctx* ctx, int B, int layer, const float* z, float* gscale, float* gshift, cudaStream_t s);
+int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s);
+int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s);
+int launch_node_h(dfm_ctx* ctx, int layer, int M, const float* z, const float* gscale, const float* gshift, float* h,
+                  __half* h16, cudaStream_t s);
 int launch_force_head(dfm_ctx* ctx, int B, const float* t, Workspace& ws, float* tr_score, float* rot_score,
                       float* f_out, cudaStream_t s);
 int launch_energy(dfm_ctx* ctx, int B, bool fp32_path, Workspace& ws, float* energy, int32_t* clashes,

@@ -163,7 +163,7 @@ struct Params {
   const float* b2;          // [256]
   const float* wa;          // [256]
   const float* ba;          // [1]
-  float* agg;               // [B*N, 256] fp32 out
+  __half* agg16;            // [B*N, 256] fp16(agg x 2^-6) out
   __half* mstar;            // [B*L, 64, 256] fp16 (m* x 2^-6), last layer only
 };
 
@@ -481,10 +481,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       asm volatile("bar.sync %0, 128;" ::"r"(5 + hn) : "memory");     // the 4 warps that hold this residue's rows
       if (node < p.total_nodes) {
         const uint32_t a0 = ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u;
-        float2 o;
-        o.x = (ldsf(a0) + ldsf(a0 + 1024u)) * (1.f / MSTAR_SCALE);
-        o.y = (ldsf(a0 + 4u) + ldsf(a0 + 1028u)) * (1.f / MSTAR_SCALE);
-        *reinterpret_cast<float2*>(p.agg + (size_t)node * H + ecol) = o;
+        // agg stays x 2^-6 in fp16 (the W3a image carries the 2^6): operand of node_tc.cu MODE_Z
+        *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
       }
     }
   }
@@ -497,8 +495,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 
 }  // namespace ews
 
-int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, const __half* Alo,
-                   cudaStream_t s) {
+int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, __half* agg16, cudaStream_t s) {
   const LayerW& w = ctx->layer[a.layer];
   ews::Params p{};
   p.total_nodes = a.B * a.N;
@@ -507,11 +504,11 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   p.last = a.last ? 1 : 0;
   p.Wimg = w.img_W2h;
   p.emeta = emeta;
-  p.Ahi = Ahi; p.Alo = Alo;
+  p.Ahi = Ahi; p.Alo = nullptr;
   p.Bm = reinterpret_cast<const __half*>(a.Bm);
   p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
   p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
-  p.agg = a.agg; p.mstar = a.mstar;
+  p.agg16 = agg16; p.mstar = a.mstar;
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));

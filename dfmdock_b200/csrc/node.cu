@@ -86,14 +86,22 @@ int launch_single_embed(dfm_ctx* ctx, const float* rec_x, const float* lig_x, cu
   return 0;
 }
 
-__global__ void k_broadcast_h0(size_t per, const float4* __restrict__ h0, float4* __restrict__ h) {
+__global__ void k_broadcast_h0(size_t per, const float4* __restrict__ h0, float4* __restrict__ h, uint2* __restrict__ h16) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < per) h[(size_t)blockIdx.y * per + idx] = h0[idx];
+  if (idx < per) {
+    const float4 v = h0[idx];
+    h[(size_t)blockIdx.y * per + idx] = v;
+    if (h16) {
+      const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      h16[(size_t)blockIdx.y * per + idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+  }
 }
 int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s) {
   const size_t per = (size_t)ctx->N * H / 4;
   dim3 grid((unsigned)((per + 255) / 256), B);
-  k_broadcast_h0<<<grid, 256, 0, s>>>(per, reinterpret_cast<const float4*>(ctx->h0), reinterpret_cast<float4*>(ws.h));
+  k_broadcast_h0<<<grid, 256, 0, s>>>(per, reinterpret_cast<const float4*>(ctx->h0), reinterpret_cast<float4*>(ws.h),
+                                      reinterpret_cast<uint2*>(ws.h16));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -136,6 +144,49 @@ __global__ void __launch_bounds__(256) k_graphnorm_silu(int N, const float* __re
     yb[(size_t)n * H + c] = silu_acc(w * o / sd + bi);
   }
 }
+// Statistics only (throughput path): gscale = weight * rstd, gshift = bias - mean*mean_scale*gscale, so that the
+// consumer (node_tc.cu MODE_H) forms SiLU(z * gscale + gshift) while it builds its operand tile.
+__global__ void __launch_bounds__(256) k_graphnorm_stats(int N, const float* __restrict__ z, const float* __restrict__ gw,
+                                                        const float* __restrict__ gb, const float* __restrict__ gms,
+                                                        float* __restrict__ gscale, float* __restrict__ gshift) {
+  const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const float* zb = z + (size_t)b * N * H;
+  __shared__ float red[8][32];
+  float s = 0.f;
+  for (int n = ry; n < N; n += 8) s += zb[(size_t)n * H + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) mean += red[q][threadIdx.x & 31];
+  mean /= (float)N;
+  const float shift = mean * gms[c];
+  __syncthreads();
+  float v = 0.f;
+  for (int n = ry; n < N; n += 8) {
+    const float o = zb[(size_t)n * H + c] - shift;
+    v = fmaf(o, o, v);
+  }
+  red[ry][threadIdx.x & 31] = v;
+  __syncthreads();
+  if (ry == 0) {
+    float var = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) var += red[q][threadIdx.x & 31];
+    var /= (float)N;
+    const float sc = gw[c] / sqrtf(var + 1e-5f);
+    gscale[(size_t)b * H + c] = sc;
+    gshift[(size_t)b * H + c] = gb[c] - shift * sc;
+  }
+}
+int launch_graphnorm_stats(dfm_ctx* ctx, int B, int layer, const float* z, float* gscale, float* gshift, cudaStream_t s) {
+  const LayerW& w = ctx->layer[layer];
+  dim3 grid(B, 8);
+  k_graphnorm_stats<<<grid, 256, 0, s>>>(ctx->N, z, w.gn_w, w.gn_b, w.gn_ms, gscale, gshift);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
   dim3 grid(B, 8);
