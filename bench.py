@@ -11,7 +11,7 @@ reverse-diffusion step of all 256 trajectories (score-network forward + SO(3)xR^
 
 Keys beyond the base contract:
   e2e          same metric through the public Python API with HOST buffers (pinned H2D of poses/times, D2H of poses/scores per step)
-  roofline     dominant kernel (fused tcgen05 edge kernel): algorithmic FLOP per launch / CUDA-event kernel time, vs the
+  roofline     dominant kernel (warp-specialised fused tcgen05 edge kernel, edge_ws.cu): algorithmic FLOP per launch / CUDA-event kernel time, vs the
                measured dense fp16/bf16 tensor peak in MEASURED_PEAKS.json (sustained figure: kernel timed inside a long step)
   cpu_baseline oracle port (the reference's algorithm, torch CPU ops as the reference writes them) on a bounded sample
   full_job     one complete config-#3 job (256 trajectories x 100 steps incl. random init and the final energy forward)
@@ -291,7 +291,7 @@ def run_cuda(args):
                     "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "kernel": "tc::k_tc<EDGE> (fused edge MLP, tcgen05)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "ews::k_edge_ws (warp-specialised fused edge MLP, tcgen05)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
                          "traffic": traffic, "peak_source": peaks["source"], "kernel_ms_per_launch": edge_avg_ms,
                          "launches_timed": edge_n, "flops_per_launch": flops_launch,

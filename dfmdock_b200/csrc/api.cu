@@ -327,7 +327,7 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
       CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], s));
       ctx->prof_used += 2;
     }
-    if (last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
+    if (last && (rc = launch_node_coord(ctx, ea, s))) return rc;
     if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
     if ((rc = launch_node_z(ctx, l, M, ws.h16, ws.agg16, ws.z, s))) return rc;
     if ((rc = launch_graphnorm_stats(ctx, B, l, ws.z, ws.gscale, ws.gshift, s))) return rc;

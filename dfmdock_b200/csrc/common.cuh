@@ -202,6 +202,7 @@ int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_stats(dfm_ctx* ctx, int B, int layer, const float* z, float* gscale, float* gshift, cudaStream_t s);
 int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s);
+int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s);
 int launch_node_h(dfm_ctx* ctx, int layer, int M, const float* z, const float* gscale, const float* gshift, float* h,
                   __half* h16, cudaStream_t s);

@@ -2,6 +2,8 @@
 //   MODE_AB  Ah = fp16((W1s h + b1)/2), Bm = fp16((W1d h)/2)   node halves of edge_mlp.0   (src/models/egnn.py:95-104)
 //   MODE_Z   z = W3h h + W3a agg + b3                           node_mlp.0 on [h, agg]      (src/models/egnn.py:106-116)
 //   MODE_H   h += W4 SiLU(GraphNorm(z)) + b4  (+ fp16 copy)     node_mlp.1-3 + residual     (src/models/egnn.py:74,106-116)
+//   MODE_C   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2), f_i = mean_k (x_i - x_j)/(|x_i - x_j| + 1) w   coord_model of the
+//            last layer, ligand rows only                                                   (src/models/egnn.py:118-148)
 //
 // fp16 activations (h16, agg16) go HBM -> shared memory with cp.async straight into the K-major SWIZZLE_128B operand
 // layout (no registers, no ALU); the 128 KB fp16 weight image is resident in shared memory; accumulators are
@@ -18,8 +20,9 @@ constexpr uint32_t W_KBLK = 256 * 128;
 constexpr uint32_t S_KBLK = TILE_M * 128;
 constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_S = W_BYTES;
-constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 256 floats bias
-constexpr uint32_t OFF_BAR = OFF_VEC + 1024;         // 2 mbarriers + tmem base
+constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 256 floats bias, 256 floats wc2
+constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // MODE_C: [4][128] dot partials, [4][4] force partials
+constexpr uint32_t OFF_BAR = OFF_PART + 2048 + 64;   // 2 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;
 constexpr int NT = 512;
@@ -88,7 +91,7 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2 };
+enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2, MODE_C = 3 };
 
 struct Params {
   int M, ntiles, N;
@@ -108,6 +111,12 @@ struct Params {
   const float* gshift;   // [B, 256]
   float* h;              // MODE_H in/out
   __half* h16;           // MODE_H out
+  // MODE_C: X = gated messages of the ligand residues [B*L, 64, 256] fp16 (x 2^-6; W0 = Wc1 x 2^6), bias0 = bc1
+  const float* wc2;      // [256]
+  const int32_t* nbr;    // [B*N, 64]
+  const float* pos;      // [B*N, 3, 3] centred backbone
+  float* fbuf;           // [B*L, 4] out
+  int R, K;
 };
 
 template <int MODE>
@@ -180,7 +189,10 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
   // ---- setup
   const __half* wimg0 = (MODE == MODE_AB && side) ? p.W1 : p.W0;
   load_weights(wimg0);
-  if (tid < 256) vbias[tid] = (MODE == MODE_AB && side) ? 0.f : (p.bias0 ? p.bias0[tid] : 0.f);
+  if (tid < 256) {
+    vbias[tid] = (MODE == MODE_AB && side) ? 0.f : (p.bias0 ? p.bias0[tid] : 0.f);
+    if (MODE == MODE_C) vbias[256 + tid] = p.wc2[tid];
+  }
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar1, 1);
@@ -263,6 +275,59 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
     tc_fence_before();
   };
 
+  // MODE_C epilogue: tile = 2 ligand residues x 64 slots (all threads take part: it synchronises the CTA)
+  auto epilogue_c = [&](int tile, int buf) {
+    float* part = reinterpret_cast<float*>(smem + OFF_PART);
+    float* fpart = part + 512;
+    const int total = p.M / SLOTS;                       // B * L residues
+    const int node = tile * 2 + (erow >> 6), k = erow & 63;
+    const bool valid = node < total && k < p.K;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cq * 64);
+    float dotp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32_issue(taddr + c * 32, v);
+      tmem_ld_wait();
+      const int col0 = cq * 64 + c * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
+    }
+    tc_fence_before();
+    part[cq * 128 + erow] = dotp;
+    __syncthreads();
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (cq == 0 && valid) {
+      const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
+      const int L = p.N - p.R;
+      const int b = node / L, i = p.R + node % L;
+      const size_t gi = (size_t)b * p.N + i;
+      const int j = __ldg(p.nbr + gi * SLOTS + k);
+      const float* pi = p.pos + gi * 9 + 3;
+      const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
+      const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+      const float rad = dx * dx + dy * dy + dz * dz;
+      const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
+      fx = dx * sc; fy = dy * sc; fz = dz * sc;
+    }
+    if (cq == 0) {
+      fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+      if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int nd = tile * 2 + tid;
+      if (nd < total) {
+        const float inv = 1.f / (float)p.K;
+        float* fo = p.fbuf + (size_t)nd * 4;
+        fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
+        fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
+        fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
+        fo[3] = 0.f;
+      }
+    }
+  };
+
   if (MODE == MODE_Z) {
     // pairs of tiles: both accumulators take the h16 pass with W3h, then the weight image is swapped to W3a for the
     // agg16 pass; z is written once.
@@ -297,7 +362,7 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
       if (ntile < p.ntiles) {
         if (MODE == MODE_H) build_h(ntile); else load_tile16(p.X, ntile);   // in flight during the epilogue below
       }
-      epilogue(tile, buf);
+      if (MODE == MODE_C) epilogue_c(tile, buf); else epilogue(tile, buf);
     }
   }
   cp_async_wait_all();
@@ -352,4 +417,14 @@ int launch_node_h(dfm_ctx* ctx, int layer, int M, const float* z, const float* g
   p.M = M; p.ntiles = (M + ntc::TILE_M - 1) / ntc::TILE_M; p.N = ctx->N;
   p.W0 = w.img_W4; p.bias0 = w.b4; p.z = z; p.gscale = gscale; p.gshift = gshift; p.h = h; p.h16 = h16;
   return ntc::launch<ntc::MODE_H>(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
+}
+
+// per-residue force of the ligand (last layer): replaces tc.cu k_tc<COORD> on the throughput path
+int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
+  const LayerW& w = ctx->layer[a.layer];
+  ntc::Params p{};
+  const int L = a.N - a.R;
+  p.M = a.B * L * SLOTS; p.ntiles = (a.B * L + 1) / 2; p.N = a.N; p.R = a.R; p.K = a.K;
+  p.X = a.mstar; p.W0 = w.img_Wc1s; p.bias0 = w.bc1; p.wc2 = w.wc2; p.nbr = a.nbr; p.pos = a.pos; p.fbuf = a.fbuf;
+  return ntc::launch<ntc::MODE_C>(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
 }
