@@ -197,7 +197,7 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = dev_alloc(ctx, &w.w1r, H))) return rc;
     if ((rc = dev_alloc(ctx, &w.b1eff, H))) return rc;
     __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1, &w.img_W2h,
-                       &w.img_Wc1s};
+                       &w.img_Wc1s, &w.img_W3z0, &w.img_W3z1};
     for (auto pp : imgs) if ((rc = dev_alloc(ctx, pp, (size_t)H * H))) return rc;
     if ((rc = launch_pair_table(ctx, l, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W1, 641, 0, 1.f, w.img_W1s, s))) return rc;
@@ -208,6 +208,7 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = launch_image_pack(ctx, w.W4, 256, 0, 1.f, w.img_W4, s))) return rc;
     if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, S_UNSCALE, w.img_Wc1, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W2, 256, 0, 0.5f, w.img_W2h, s))) return rc;
+    if ((rc = launch_image_pack_z(ctx, w.W3, AGG_UNSCALE, w.img_W3z0, w.img_W3z1, s))) return rc;
     if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, 64.f, w.img_Wc1s, s))) return rc;
   }
   NEED("to_energy.0.weight", {H, 2 * H}); ctx->We = tmp;

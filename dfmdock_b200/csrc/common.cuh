@@ -87,6 +87,8 @@ struct LayerW {
   __half* Totp16h;      // Totp16 / 2
   __half* img_W2h;      // W2 / 2
   __half* img_Wc1s;     // Wc1 x 2^6 (gated messages are spilled x 2^-6)
+  __half* img_W3z0;     // [W3h | W3a x 2^6] rows 0-127, K = 512 (node_tc.cu MODE_Z)
+  __half* img_W3z1;     // rows 128-255
 };
 
 struct dfm_ctx {
@@ -202,6 +204,7 @@ int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_stats(dfm_ctx* ctx, int B, int layer, const float* z, float* gscale, float* gshift, cudaStream_t s);
 int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s);
+int launch_image_pack_z(dfm_ctx* ctx, const float* W3, float scale_hi, __half* img0, __half* img1, cudaStream_t s);
 int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s);
 int launch_node_h(dfm_ctx* ctx, int layer, int M, const float* z, const float* gscale, const float* gshift, float* h,

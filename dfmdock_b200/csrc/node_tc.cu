@@ -1,32 +1,34 @@
-// Node-side tcgen05 kernels of the throughput path (per-residue 256x256 contractions, HBM-bound):
+// Node-side tcgen05 kernels of the throughput path (per-residue contractions with 256-wide operands, HBM-bound):
 //   MODE_AB  Ah = fp16((W1s h + b1)/2), Bm = fp16((W1d h)/2)   node halves of edge_mlp.0   (src/models/egnn.py:95-104)
 //   MODE_Z   z = W3h h + W3a agg + b3                           node_mlp.0 on [h, agg]      (src/models/egnn.py:106-116)
 //   MODE_H   h += W4 SiLU(GraphNorm(z)) + b4  (+ fp16 copy)     node_mlp.1-3 + residual     (src/models/egnn.py:74,106-116)
 //   MODE_C   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2), f_i = mean_k (x_i - x_j)/(|x_i - x_j| + 1) w   coord_model of the
 //            last layer, ligand rows only                                                   (src/models/egnn.py:118-148)
 //
-// fp16 activations (h16, agg16) go HBM -> shared memory with cp.async straight into the K-major SWIZZLE_128B operand
-// layout (no registers, no ALU); the 128 KB fp16 weight image is resident in shared memory; accumulators are
-// double buffered in TMEM so that the epilogue of tile t overlaps the loads of tile t+1.  MODE_Z swaps the weight
-// image (W3h -> W3a) between the two accumulation passes of a pair of tiles instead of writing z twice.
+// One persistent CTA per SM, 19 warps:
+//   warps 0-15  workers: epilogue from TMEM (all modes); MODE_H also builds its operand (GraphNorm + SiLU of z) here
+//   warps 16-17 loaders: fp16 activations HBM -> shared memory with cp.async, straight into the K-major SWIZZLE_128B
+//               operand layout, one 64-column K block (16 KB) at a time into a ring of four blocks
+//   warp  18    MMA issuer: one tcgen05.commit per K block (frees the ring slot) and one per tile (accumulator ready)
+// The 128 KB fp16 weight image is resident in shared memory.  MODE_Z contracts over K = 512 ([h | agg]) with the
+// output columns split over the two halves of the grid (N = 128 per CTA), so z is written once and no weight swap is
+// needed; the other modes use N = 256, K = 256.  Accumulators are double buffered in TMEM.
 #include "common.cuh"
 
 namespace ntc {
 
 constexpr int TILE_M = 128;
-constexpr uint32_t W_BYTES = 256 * 256 * 2;
-constexpr uint32_t S_BYTES = TILE_M * 256 * 2;
-constexpr uint32_t W_KBLK = 256 * 128;
-constexpr uint32_t S_KBLK = TILE_M * 128;
+constexpr uint32_t W_BYTES = 256 * 256 * 2;          // 128 KB in every mode (256 x 256 or 128 x 512 fp16)
+constexpr uint32_t S_KBLK = TILE_M * 128;            // one K block of the operand tile: 128 rows x 64 fp16
 constexpr uint32_t OFF_W = 0;
-constexpr uint32_t OFF_S = W_BYTES;
-constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // 256 floats bias, 256 floats wc2
+constexpr uint32_t OFF_S = W_BYTES;                  // ring of 4 K blocks
+constexpr uint32_t OFF_VEC = OFF_S + 4 * S_KBLK;     // 256 floats bias, 256 floats wc2
 constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // MODE_C: [4][128] dot partials, [4][4] force partials
-constexpr uint32_t OFF_BAR = OFF_PART + 2048 + 64;   // 2 mbarriers + tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t OFF_BAR = OFF_PART + 2048 + 64;   // full[4], empty[4], accf[2], acce[2], tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;
-constexpr int NT = 512;
-constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int NWORK = 16;
+constexpr int NT = (NWORK + 3) * 32;                 // 608
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -35,23 +37,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, tries = 0;
-  do {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  while (!ok) {
+    __nanosleep(40);
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++tries > (1u << 24)) __trap();
-  } while (!ok);
+    if (++tries > (1u << 24)) __trap();   // a lost arrival must fail loudly, never hang the GPU
+  }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -71,10 +80,6 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ uint32_t s_off(int r, int c16) {
-  return (uint32_t)(c16 >> 3) * S_KBLK + (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
 }
 __device__ __forceinline__ uint4 pack8(const float* x) {
   __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
@@ -96,8 +101,10 @@ enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2, MODE_C = 3 };
 struct Params {
   int M, ntiles, N;
   // MODE_AB: X = h16; CTAs [0, grid/2) use W0/bias0/out0, the rest W1/(no bias)/out1; out = fp16(0.5 * (acc + bias))
-  // MODE_Z : pass 1 X = h16 with W0, pass 2 X2 = agg16 with W1; out32 = acc + bias0
+  // MODE_Z : K blocks 0-3 from X = h16, 4-7 from X2 = agg16; CTAs [0, grid/2) use W0 (output columns 0-127), the
+  //          rest W1 (columns 128-255); out32[:, half] = acc + bias0[half]
   // MODE_H : operand = fp16(SiLU(z * gscale[b] + gshift[b])) with W0; h = h + acc + bias0; also h16
+  // MODE_C : X = gated messages of the ligand residues [B*L, 64, 256] fp16 (x 2^-6; W0 = Wc1 x 2^6), bias0 = bc1
   const __half* X;
   const __half* X2;
   const __half* W0;
@@ -106,12 +113,11 @@ struct Params {
   __half* out0;
   __half* out1;
   float* out32;
-  const float* z;        // MODE_H
+  const float* z;
   const float* gscale;   // [B, 256]
   const float* gshift;   // [B, 256]
-  float* h;              // MODE_H in/out
-  __half* h16;           // MODE_H out
-  // MODE_C: X = gated messages of the ligand residues [B*L, 64, 256] fp16 (x 2^-6; W0 = Wc1 x 2^6), bias0 = bc1
+  float* h;
+  __half* h16;
   const float* wc2;      // [256]
   const int32_t* nbr;    // [B*N, 64]
   const float* pos;      // [B*N, 3, 3] centred backbone
@@ -121,254 +127,278 @@ struct Params {
 
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
+  constexpr int KB = (MODE == MODE_Z) ? 8 : 4;            // K blocks per tile
+  constexpr int NCOL = (MODE == MODE_Z) ? 128 : 256;      // accumulator columns per tile
+  constexpr uint32_t W_KBLK = NCOL * 128;                 // bytes per K block of the weight image
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr bool SPLIT = (MODE == MODE_AB || MODE == MODE_Z);   // the two halves of the grid use different weights
+
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* vbias = reinterpret_cast<float*>(smem + OFF_VEC);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
-  const uint32_t bar0 = sbase + OFF_BAR, bar1 = sbase + OFF_BAR + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 32;
+  const uint32_t bar_accf = sbase + OFF_BAR + 64, bar_acce = sbase + OFF_BAR + 80;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // which half of the grid (MODE_AB only)
   const int half_grid = (int)gridDim.x >> 1;
-  const int side = (MODE == MODE_AB && (int)blockIdx.x >= half_grid) ? 1 : 0;
-  const int cta = (MODE == MODE_AB) ? ((int)blockIdx.x - side * half_grid) : (int)blockIdx.x;
-  const int ncta = (MODE == MODE_AB) ? half_grid : (int)gridDim.x;
+  const int side = (SPLIT && (int)blockIdx.x >= half_grid) ? 1 : 0;
+  const int cta = SPLIT ? ((int)blockIdx.x - side * half_grid) : (int)blockIdx.x;
+  const int ncta = SPLIT ? half_grid : (int)gridDim.x;
 
-  auto load_weights = [&](const __half* img) {
-    const char* src = reinterpret_cast<const char*>(img);
-#pragma unroll 4
-    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) cp_async16(sbase + OFF_W + (uint32_t)i * 16u, src + (size_t)i * 16, 16u);
-  };
-  auto load_tile16 = [&](const __half* X, int tile) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = tid + NT * i;
-      const int r = idx >> 5, c16 = idx & 31;
-      const int m = tile * TILE_M + r;
-      const bool ok = m < p.M;
-      cp_async16(sbase + OFF_S + s_off(r, c16), X + (size_t)(ok ? m : 0) * H + c16 * 8, ok ? 16u : 0u);
+  // ---- setup: weight image (plain loads; visible to the tensor core after the fence below), vectors, barriers, TMEM
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(side ? p.W1 : p.W0);
+    uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
+    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
+    if (tid < 256) {
+      float b = p.bias0 ? p.bias0[tid] : 0.f;
+      if (MODE == MODE_AB && side) b = 0.f;
+      vbias[tid] = b;
+      if (MODE == MODE_C) vbias[256 + tid] = p.wc2[tid];
     }
-  };
-  // MODE_H operand: y = SiLU(z * scale + shift) -> fp16; one warp per row, 8 columns per lane, 4 rows in flight
-  auto build_h = [&](int tile) {
-#pragma unroll 1
-    for (int r4 = 0; r4 < 8; r4 += 4) {   // 8 rows per warp (128 rows / 16 warps), 4 at a time
-      float4 z0[4], z1[4];
-      int mrow[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp + 16 * (r4 + i);
-        const int m = tile * TILE_M + r;
-        mrow[i] = m;
-        z0[i] = make_float4(0.f, 0.f, 0.f, 0.f); z1[i] = z0[i];
-        if (m < p.M) {
-          const float4* zp = reinterpret_cast<const float4*>(p.z + (size_t)m * H + lane * 8);
-          z0[i] = __ldg(zp); z1[i] = __ldg(zp + 1);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp + 16 * (r4 + i);
-        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (mrow[i] < p.M) {
-          const int b = mrow[i] / p.N;
-          const float4* sc = reinterpret_cast<const float4*>(p.gscale + (size_t)b * H + lane * 8);
-          const float4* sh = reinterpret_cast<const float4*>(p.gshift + (size_t)b * H + lane * 8);
-          const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
-          x[0] = silu_tanh(fmaf(z0[i].x, s0.x, h0.x)); x[1] = silu_tanh(fmaf(z0[i].y, s0.y, h0.y));
-          x[2] = silu_tanh(fmaf(z0[i].z, s0.z, h0.z)); x[3] = silu_tanh(fmaf(z0[i].w, s0.w, h0.w));
-          x[4] = silu_tanh(fmaf(z1[i].x, s1.x, h1.x)); x[5] = silu_tanh(fmaf(z1[i].y, s1.y, h1.y));
-          x[6] = silu_tanh(fmaf(z1[i].z, s1.z, h1.z)); x[7] = silu_tanh(fmaf(z1[i].w, s1.w, h1.w));
-        }
-        *reinterpret_cast<uint4*>(smem + OFF_S + s_off(r, lane)) = pack8(x);
-      }
-    }
-  };
-
-  // ---- setup
-  const __half* wimg0 = (MODE == MODE_AB && side) ? p.W1 : p.W0;
-  load_weights(wimg0);
-  if (tid < 256) {
-    vbias[tid] = (MODE == MODE_AB && side) ? 0.f : (p.bias0 ? p.bias0[tid] : 0.f);
-    if (MODE == MODE_C) vbias[256 + tid] = p.wc2[tid];
   }
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar1, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == NWORK + 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint64_t dW = make_desc(sbase + OFF_W);
-  const uint64_t dS = make_desc(sbase + OFF_S);
-  const int q = warp & 3, cq = warp >> 2;
-  const int erow = q * 32 + lane;
-  uint32_t ph0 = 0, ph1 = 0;     // parities of the next completion of bar0 / bar1
 
-  auto issue_mma = [&](int buf, uint32_t accumulate) {   // call from one thread after the operands are visible
-    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+  if (warp == NWORK + 2) {
+    // =================================== MMA ISSUER ===================================================
+    if (lane == 0) {
+      const uint64_t dW = make_desc(sbase + OFF_W);
+      const uint64_t dS = make_desc(sbase + OFF_S);
+      int it = 0;
+      uint32_t c = 0;                                        // running K-block count -> ring slot / phase
+      for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NCOL);
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb, ++c) {
+          const uint32_t slot = c & 3u;
+          mbar_wait(bar_full + 8 * slot, (c >> 2) & 1u);
+          tc_fence_after();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const uint64_t da = dS + (uint64_t)(((kk >> 2) * S_KBLK + (kk & 3) * 32) >> 4);
-      const uint64_t db = dW + (uint64_t)(((kk >> 2) * W_KBLK + (kk & 3) * 32) >> 4);
-      mma_f16(d_tmem, da, db, (accumulate | (uint32_t)kk) ? 1u : 0u);
-    }
-    mma_commit(buf ? bar1 : bar0);
-  };
-  auto wait_mma = [&](int buf) {
-    if (buf) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
-    tc_fence_after();
-  };
-  // operands written by cp.async / st.shared -> visible to the tensor core, then one thread issues
-  auto publish_and_mma = [&](int buf, uint32_t accumulate) {
-    cp_async_wait_all();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma(buf, accumulate);
-    }
-  };
-  auto epilogue = [&](int tile, int buf) {
-    const int mrow = tile * TILE_M + erow;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cq * 64);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32_issue(taddr + c * 32, v);
-      tmem_ld_wait();
-      if (mrow < p.M) {
-        const int col0 = cq * 64 + c * 32;
-        const size_t o = (size_t)mrow * H + col0;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] += vbias[col0 + e];
-        if (MODE == MODE_AB) {
-          __half* out = side ? p.out1 : p.out0;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] *= 0.5f;
-#pragma unroll
-          for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(out + o + e8 * 8) = pack8(v + e8 * 8);
-        } else if (MODE == MODE_Z) {
-#pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4)
-            *reinterpret_cast<float4*>(p.out32 + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 hv = *reinterpret_cast<const float4*>(p.h + o + e4 * 4);
-            v[e4 * 4] += hv.x; v[e4 * 4 + 1] += hv.y; v[e4 * 4 + 2] += hv.z; v[e4 * 4 + 3] += hv.w;
-            *reinterpret_cast<float4*>(p.h + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t da = dS + (uint64_t)((slot * S_KBLK + k4 * 32) >> 4);
+            const uint64_t db = dW + (uint64_t)(((uint32_t)kb * W_KBLK + k4 * 32) >> 4);
+            mma_f16(d_tmem, da, db, IDESC, (kb | k4) ? 1u : 0u);
           }
-#pragma unroll
-          for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(p.h16 + o + e8 * 8) = pack8(v + e8 * 8);
+          mma_commit(bar_empty + 8 * slot);
         }
+        mma_commit(bar_accf + 8 * buf);
       }
     }
-    tc_fence_before();
-  };
-
-  // MODE_C epilogue: tile = 2 ligand residues x 64 slots (all threads take part: it synchronises the CTA)
-  auto epilogue_c = [&](int tile, int buf) {
-    float* part = reinterpret_cast<float*>(smem + OFF_PART);
-    float* fpart = part + 512;
-    const int total = p.M / SLOTS;                       // B * L residues
-    const int node = tile * 2 + (erow >> 6), k = erow & 63;
-    const bool valid = node < total && k < p.K;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cq * 64);
-    float dotp = 0.f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32_issue(taddr + c * 32, v);
-      tmem_ld_wait();
-      const int col0 = cq * 64 + c * 32;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
-    }
-    tc_fence_before();
-    part[cq * 128 + erow] = dotp;
-    __syncthreads();
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (cq == 0 && valid) {
-      const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
-      const int L = p.N - p.R;
-      const int b = node / L, i = p.R + node % L;
-      const size_t gi = (size_t)b * p.N + i;
-      const int j = __ldg(p.nbr + gi * SLOTS + k);
-      const float* pi = p.pos + gi * 9 + 3;
-      const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
-      const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
-      const float rad = dx * dx + dy * dy + dz * dz;
-      const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
-      fx = dx * sc; fy = dy * sc; fz = dz * sc;
-    }
-    if (cq == 0) {
-      fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-      if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
-    }
-    __syncthreads();
-    if (tid < 2) {
-      const int nd = tile * 2 + tid;
-      if (nd < total) {
-        const float inv = 1.f / (float)p.K;
-        float* fo = p.fbuf + (size_t)nd * 4;
-        fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
-        fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
-        fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
-        fo[3] = 0.f;
-      }
-    }
-  };
-
-  if (MODE == MODE_Z) {
-    // pairs of tiles: both accumulators take the h16 pass with W3h, then the weight image is swapped to W3a for the
-    // agg16 pass; z is written once.
-    bool w_is_0 = true;
-    for (int t0 = cta * 2; t0 < p.ntiles; t0 += ncta * 2) {
-      const int nt = (t0 + 1 < p.ntiles) ? 2 : 1;
-      for (int pass = 0; pass < 2; ++pass) {
-        if ((pass == 0) != w_is_0) {          // previous MMAs that read the old image have completed (waited below)
-          load_weights(pass == 0 ? p.W0 : p.W1);
-          w_is_0 = (pass == 0);
-        }
-        for (int u = 0; u < nt; ++u) {
-          load_tile16(pass == 0 ? p.X : p.X2, t0 + u);
-          publish_and_mma(u, pass ? 1u : 0u);
-          wait_mma(u);                        // S (and W) may be overwritten
+    __syncwarp();
+  } else if (warp >= NWORK) {
+    // =================================== LOADERS ======================================================
+    if (MODE != MODE_H) {
+      const int lw = warp - NWORK;                           // loader 0 takes even K blocks, loader 1 odd ones
+      const int c8 = lane & 7, rsub = lane >> 3;
+      uint32_t c = 0;
+      for (int tile = cta; tile < p.ntiles; tile += ncta) {
+        const int row0 = tile * TILE_M;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb, ++c) {
+          if ((kb & 1) != lw) continue;
+          const uint32_t slot = c & 3u;
+          if (c >= 4) mbar_wait(bar_empty + 8 * slot, ((c >> 2) - 1) & 1u);
+          const __half* X = (MODE == MODE_Z && kb >= 4) ? p.X2 : p.X;
+          const int kcol = (kb & 3) * 64 + c8 * 8;
+          const uint32_t dst0 = sbase + OFF_S + slot * S_KBLK;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int r = rsub + 4 * i;
+            const int m = row0 + r;
+            const bool ok = m < p.M;
+            cp_async16(dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4), X + (size_t)(ok ? m : 0) * H + kcol, ok ? 16u : 0u);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * slot) : "memory");
         }
       }
-      for (int u = 0; u < nt; ++u) epilogue(t0 + u, u);
-      __syncthreads();                        // accumulators drained before the next pair's first MMA overwrites them
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    __syncwarp();
   } else {
-    int it = 0;
-    int tile = cta;
-    if (tile < p.ntiles) {
-      if (MODE == MODE_H) build_h(tile); else load_tile16(p.X, tile);
-    }
-    for (; tile < p.ntiles; tile += ncta, ++it) {
-      const int buf = it & 1;
-      publish_and_mma(buf, 0u);
-      wait_mma(buf);
-      const int ntile = tile + ncta;
-      if (ntile < p.ntiles) {
-        if (MODE == MODE_H) build_h(ntile); else load_tile16(p.X, ntile);   // in flight during the epilogue below
+    // =================================== WORKERS ======================================================
+    const int q = warp & 3, cq = warp >> 2;                  // TMEM lane quarter / column quarter
+    const int erow = q * 32 + lane;
+    constexpr int CW = NCOL / 4;                             // accumulator columns per thread (64 or 32)
+    uint32_t cb = 0;                                         // MODE_H: running K-block count of the builds
+
+    // MODE_H operand: y = SiLU(z * gscale[b] + gshift[b]) -> fp16, one K block (64 columns) at a time;
+    // 8 lanes per row (8 columns each), 4 rows per warp instruction, 8 rows per warp and K block
+    auto build_h = [&](int tile) {
+      const int c8 = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+      for (int kb = 0; kb < 4; ++kb, ++cb) {
+        const uint32_t slot = cb & 3u;
+        const int col = kb * 64 + c8 * 8;
+        float4 z0[2], z1[2];
+        int mrow[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = warp * 8 + 4 * i + rsub;
+          const int m = tile * TILE_M + r;
+          mrow[i] = m;
+          z0[i] = make_float4(0.f, 0.f, 0.f, 0.f); z1[i] = z0[i];
+          if (m < p.M) {
+            const float4* zp = reinterpret_cast<const float4*>(p.z + (size_t)m * H + col);
+            z0[i] = __ldg(zp); z1[i] = __ldg(zp + 1);
+          }
+        }
+        if (cb >= 4) mbar_wait(bar_empty + 8 * slot, ((cb >> 2) - 1) & 1u);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = warp * 8 + 4 * i + rsub;
+          float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (mrow[i] < p.M) {
+            const int b = mrow[i] / p.N;
+            const float4* sc = reinterpret_cast<const float4*>(p.gscale + (size_t)b * H + col);
+            const float4* sh = reinterpret_cast<const float4*>(p.gshift + (size_t)b * H + col);
+            const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
+            x[0] = silu_tanh(fmaf(z0[i].x, s0.x, h0.x)); x[1] = silu_tanh(fmaf(z0[i].y, s0.y, h0.y));
+            x[2] = silu_tanh(fmaf(z0[i].z, s0.z, h0.z)); x[3] = silu_tanh(fmaf(z0[i].w, s0.w, h0.w));
+            x[4] = silu_tanh(fmaf(z1[i].x, s1.x, h1.x)); x[5] = silu_tanh(fmaf(z1[i].y, s1.y, h1.y));
+            x[6] = silu_tanh(fmaf(z1[i].z, s1.z, h1.z)); x[7] = silu_tanh(fmaf(z1[i].w, s1.w, h1.w));
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_S + slot * S_KBLK + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4)) = pack8(x);
+        }
+        fence_async_smem();
+        mbar_arrive(bar_full + 8 * slot);
       }
-      if (MODE == MODE_C) epilogue_c(tile, buf); else epilogue(tile, buf);
+    };
+
+    auto epilogue = [&](int tile, int buf) {
+      const int mrow = tile * TILE_M + erow;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NCOL + cq * CW);
+      float dotp = 0.f;
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) {
+        float v[32];
+        tmem_ld32_issue(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (c == CW / 32 - 1) {               // all TMEM reads of this thread are done: release the accumulator buffer
+          tc_fence_before();
+          mbar_arrive(bar_acce + 8 * buf);
+        }
+        const int col0 = cq * CW + c * 32;                         // column inside this CTA's accumulator
+        const int gcol0 = (MODE == MODE_Z ? side * 128 : 0) + col0; // column of the [M, 256] output
+        if (MODE == MODE_C) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
+        } else if (mrow < p.M) {
+          const size_t o = (size_t)mrow * H + gcol0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] += vbias[gcol0 + e];
+          if (MODE == MODE_AB) {
+            __half* out = side ? p.out1 : p.out0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] *= 0.5f;
+#pragma unroll
+            for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(out + o + e8 * 8) = pack8(v + e8 * 8);
+          } else if (MODE == MODE_Z) {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4)
+              *reinterpret_cast<float4*>(p.out32 + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 hv = *reinterpret_cast<const float4*>(p.h + o + e4 * 4);
+              v[e4 * 4] += hv.x; v[e4 * 4 + 1] += hv.y; v[e4 * 4 + 2] += hv.z; v[e4 * 4 + 3] += hv.w;
+              *reinterpret_cast<float4*>(p.h + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+            }
+#pragma unroll
+            for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(p.h16 + o + e8 * 8) = pack8(v + e8 * 8);
+          }
+        }
+      }
+      if (MODE == MODE_C) {
+        // tile = 2 ligand residues x 64 slots: clamp(dot) -> displacement along x_i - x_j -> mean over the K slots
+        float* part = reinterpret_cast<float*>(smem + OFF_PART);
+        float* fpart = part + 512;
+        const int total = p.M / SLOTS;                       // B * L residues
+        const int node = tile * 2 + (erow >> 6), k = erow & 63;
+        const bool valid = node < total && k < p.K;
+        part[cq * 128 + erow] = dotp;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (cq == 0 && valid) {
+          const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
+          const int L = p.N - p.R;
+          const int b = node / L, i = p.R + node % L;
+          const size_t gi = (size_t)b * p.N + i;
+          const int j = __ldg(p.nbr + gi * SLOTS + k);
+          const float* pi = p.pos + gi * 9 + 3;
+          const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
+          const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+          const float rad = dx * dx + dy * dy + dz * dz;
+          const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
+          fx = dx * sc; fy = dy * sc; fz = dz * sc;
+        }
+        if (cq == 0) {
+          fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+          if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < 2) {
+          const int nd = tile * 2 + tid;
+          if (nd < total) {
+            const float inv = 1.f / (float)p.K;
+            float* fo = p.fbuf + (size_t)nd * 4;
+            fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
+            fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
+            fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
+            fo[3] = 0.f;
+          }
+        }
+      }
+    };
+
+    int it = 0;
+    if (MODE == MODE_H) {
+      // build(t) -> epilogue(t-1) -> build(t+1) ...: the MMA of tile t runs under the epilogue of tile t-1
+      int prev = -1;
+      for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+        build_h(tile);
+        if (prev >= 0) {
+          const int pb = (it - 1) & 1;
+          mbar_wait(bar_accf + 8 * pb, (uint32_t)(((it - 1) >> 1) & 1));
+          tc_fence_after();
+          epilogue(prev, pb);
+        }
+        prev = tile;
+      }
+      if (prev >= 0) {
+        const int pb = (it - 1) & 1;
+        mbar_wait(bar_accf + 8 * pb, (uint32_t)(((it - 1) >> 1) & 1));
+        tc_fence_after();
+        epilogue(prev, pb);
+      }
+    } else {
+      for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        epilogue(tile, buf);
+      }
     }
   }
-  cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == NWORK + 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
@@ -388,6 +418,22 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
 
 }  // namespace ntc
 
+// fp16 image of W3 = [W3h | W3a x 2^6] (K = 512) for one half of the output columns, K-major SWIZZLE_128B:
+// 8 K blocks of [128 rows x 128 B]; 16-byte chunk c of row n sits at chunk c ^ (n & 7).
+__global__ void k_image_pack_z(const float* __restrict__ W3, int half, float scale_hi, __half* __restrict__ img) {
+  const int n = blockIdx.x, k = threadIdx.x + blockIdx.y * 256;      // n in [0,128), k in [0,512)
+  const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+  const float v = W3[(size_t)(half * 128 + n) * 512 + k] * (k >= 256 ? scale_hi : 1.f);
+  img[(((size_t)kb * 128 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(v);
+}
+int launch_image_pack_z(dfm_ctx* ctx, const float* W3, float scale_hi, __half* img0, __half* img1, cudaStream_t s) {
+  k_image_pack_z<<<dim3(128, 2), 256, 0, s>>>(W3, 0, scale_hi, img0);
+  LAUNCH_CHECK(ctx);
+  k_image_pack_z<<<dim3(128, 2), 256, 0, s>>>(W3, 1, scale_hi, img1);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 // Ah = fp16((W1s h + b1eff)/2) and Bm = fp16((W1d h)/2) in one launch (two halves of the grid)
 int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
@@ -399,14 +445,15 @@ int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah
   return ntc::launch<ntc::MODE_AB>(ctx, p, 2 * half, s);
 }
 
-// z = W3h h + W3a agg + b3 (agg16 carries agg x 2^-6, img_W3a carries W3a x 2^6)
+// z = W3h h + W3a agg + b3 (agg16 carries agg x 2^-6, the image carries W3a x 2^6)
 int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
   ntc::Params p{};
   p.M = M; p.ntiles = (M + ntc::TILE_M - 1) / ntc::TILE_M; p.N = ctx->N;
-  p.X = h16; p.X2 = agg16; p.W0 = w.img_W3h; p.W1 = w.img_W3a; p.bias0 = w.b3; p.out32 = z;
-  const int pairs = (p.ntiles + 1) / 2;
-  return ntc::launch<ntc::MODE_Z>(ctx, p, pairs < ctx->num_sms ? pairs : ctx->num_sms, s);
+  p.X = h16; p.X2 = agg16; p.W0 = w.img_W3z0; p.W1 = w.img_W3z1; p.bias0 = w.b3; p.out32 = z;
+  int half = ctx->num_sms / 2;
+  if (half > p.ntiles) half = p.ntiles;
+  return ntc::launch<ntc::MODE_Z>(ctx, p, 2 * half, s);
 }
 
 // h += W4 SiLU(z * gscale + gshift) + b4; h16 = fp16(h)
