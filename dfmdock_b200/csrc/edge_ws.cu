@@ -14,6 +14,7 @@
 //
 // All operands are pre-halved at production (A, B, tables, w1r, W2, b2 carry a factor 1/2), because
 // SiLU(x) = h + h * tanh(h) with h = x/2: one MUFU and one HFMA2 per element pair.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -32,7 +33,8 @@ constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [<=4 column groups][128 
 constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [2 tile parities][4 lane quarters][256] float column sums
 constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [16 producer warps][2 slots][8 rows] int4 edge metadata
 constexpr uint32_t OFF_JRING = OFF_META + 16 * 2 * 8 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
-constexpr uint32_t OFF_BAR = OFF_JRING + 2 * 2 * 128 * 4;  // 16 mbarriers + tmem base
+constexpr uint32_t OFF_VEC32 = OFF_JRING + 2 * 2 * 128 * 4; // b2/2 [256] float, wa [256] float (fp32 epilogue)
+constexpr uint32_t OFF_BAR = OFF_VEC32 + 2048;            // 16 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 160;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
 
@@ -44,6 +46,15 @@ constexpr int NT = (NPROD + NEPI + 4) * 32;   // 896 -> 72 registers/thread at l
 constexpr int PROD_REGS = 64;            // setmaxnreg: 16*32*64 + 8*32*104 + 4*32*40 = 64512 <= 64512
 constexpr int EPI_REGS = 104;
 constexpr int MMA_REGS = 40;
+#ifndef EWS_EXP
+#define EWS_EXP 0      // diagnostic experiments (wrong results): 1 = B rows from row 0, 2 = table rows from row 0, 4 = no tanh
+#endif
+#ifndef EWS_EPI_FP32
+#define EWS_EPI_FP32 0  // epilogue SiLU and gate logit in fp32 (tanh.approx.f32), packed to half2 only for the gate / segment sum
+#endif
+#ifndef EWS_TIMING
+#define EWS_TIMING 0   // 1: accumulate cycles spent in barrier waits per role into Params::timing (diagnostic builds)
+#endif
 #ifndef EWS_USE_ALO
 #define EWS_USE_ALO 0     // carry A_i as fp16 hi + lo (1) or a single fp16 (0)
 #endif
@@ -64,13 +75,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // try_wait parks the thread inside the instruction for a hardware-bounded time; between retries back off so that
 // waiting warps do not eat the issue slots of the working warps.  A lost arrival traps instead of hanging the GPU.
+#if EWS_TIMING
+#define TWAIT(acc, call) do { const long long _t0 = clock64(); call; acc += (unsigned long long)(clock64() - _t0); } while (0)
+#else
+#define TWAIT(acc, call) do { call; } while (0)
+#endif
+template <int SLEEP_NS = 40>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, tries = 0;
   asm volatile(
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   while (!ok) {
-    __nanosleep(40);
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -145,10 +162,11 @@ __device__ __forceinline__ float2 h2f2(uint32_t a) {
   return __half22float2(*reinterpret_cast<const __half2*>(&a));
 }
 // SiLU(2h) = h + h * tanh(h)
-__device__ __forceinline__ uint32_t h2silu(uint32_t h) { return h2fma(h, h2tanh(h), h); }
+__device__ __forceinline__ uint32_t h2silu(uint32_t h) { return (EWS_EXP & 4) ? h2fma(h, h, h) : h2fma(h, h2tanh(h), h); }
 
 struct Params {
   int ntiles;
+  int chunk;                // tiles per CTA: CTA c owns the contiguous tiles [c * chunk, (c + 1) * chunk)
   int total_nodes;          // B * N
   int N, R, K;
   int last;                 // spill gated messages of ligand residues (coordinate head input)
@@ -165,6 +183,8 @@ struct Params {
   const float* ba;          // [1]
   __half* agg16;            // [B*N, 256] fp16(agg x 2^-6) out
   __half* mstar;            // [B*L, 64, 256] fp16 (m* x 2^-6), last layer only
+  unsigned long long* timing;   // EWS_TIMING: [8] cycles {prod wait bfull, prod total, loader wait empty, loader total,
+                                //                        mma wait full, mma wait acce, epi wait accf, epi total}
 };
 
 constexpr float RAD_SCALE = 0.03125f;     // radial is carried as fp16(radial / 32); w1r' = 32 * w1r / 2
@@ -210,6 +230,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       vb2[tid] = __float2half_rn(0.5f * p.b2[tid]);
       vwa[tid] = __float2half_rn(p.wa[tid]);
       vwr[tid] = __float2half_rn(p.w1r[tid] * (0.5f / RAD_SCALE));
+      reinterpret_cast<float*>(smem + OFF_VEC32)[tid] = 0.5f * p.b2[tid];
+      reinterpret_cast<float*>(smem + OFF_VEC32)[256 + tid] = p.wa[tid];
     }
   }
   if (tid == 0) {
@@ -227,6 +249,10 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // contiguous tile ranges: concurrently running CTAs work on different trajectories, so the gathered B_j rows are
+  // not hot lines shared by all SMs (strided assignment had every SM hammer the same 300 rows at the same time)
+  const int t_begin = (int)blockIdx.x * p.chunk;
+  const int t_end = min(p.ntiles, t_begin + p.chunk);
 
   if (warp < NPROD) {
     // =================================== PRODUCERS ===================================================
@@ -254,7 +280,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint4 mt = lds128(mslot + (uint32_t)(4 * i + rsub) * 16u);
+        uint4 mt = lds128(mslot + (uint32_t)(4 * i + rsub) * 16u);
+        if (EWS_EXP & 2) { mt.y = 0; mt.z = ((int)mt.z >= 0) ? 0u : mt.z; }
         g.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)mt.y * H + colh));
         g.to[i] = make_uint4(0, 0, 0, 0);
         if ((int)mt.z >= 0) g.to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)mt.z * H + colh));
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       int4 mt = pad_meta;
       const int r = warp * 8 + (lane & 7);
       const int node = tile * 2 + (r >> 6);
-      if (tile < p.ntiles && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
+      if (tile < t_end && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
       return mt;
     };
     auto a_node = [&](int tile) -> size_t {
@@ -288,46 +315,47 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       return (size_t)node * H + c8 * 8;
     };
     GBuf g0, g1;
-    const int4 pad_rad0 = pad_meta;
-    (void)pad_rad0;
-    if ((int)blockIdx.x < p.ntiles) {
-      const int4 m0 = load_meta(blockIdx.x);
+    unsigned long long tw0 = 0;
+    const long long tstart = clock64();
+    if (t_begin < t_end) {
+      const int4 m0 = load_meta(t_begin);
       if (lane < 8) sts128(mring_s + (uint32_t)lane * 16u, make_uint4(m0.x, m0.y, m0.z, m0.w));
       __syncwarp();
-      issue(g0, mring_s, a_node(blockIdx.x), 0);
+      issue(g0, mring_s, a_node(t_begin), 0);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const uint32_t mcur = mring_s + (uint32_t)(it & 1) * 128u;
       const uint32_t mnext = mring_s + (uint32_t)((it & 1) ^ 1) * 128u;
-      const int ntile = tile + (int)gridDim.x;
-      const bool has_next = ntile < p.ntiles;
+      const int ntile = tile + 1;
+      const bool has_next = ntile < t_end;
       const int4 nm = load_meta(ntile);
       const size_t ao = a_node(tile), aon = a_node(has_next ? ntile : tile);
       const uint32_t par = (uint32_t)(it & 1);
       // kb 0 (buffer 0); prefetch kb 1
       issue(g1, mcur, ao, 1);
-      mbar_wait(bar_bfull + 0, par);
+      TWAIT(tw0, mbar_wait<100>(bar_bfull + 0, par));
       compute(g0, mcur, 0);
       fence_async_smem(); mbar_arrive(bar_full + 0);
       // kb 1 (buffer 1); prefetch kb 2
       issue(g0, mcur, ao, 2);
-      mbar_wait(bar_bfull + 8, par);
+      TWAIT(tw0, mbar_wait<100>(bar_bfull + 8, par));
       compute(g1, mcur, 1);
       fence_async_smem(); mbar_arrive(bar_full + 8);
-      if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
-      __syncwarp();
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
-      mbar_wait(bar_bfull + 16, par);
+      TWAIT(tw0, mbar_wait<100>(bar_bfull + 16, par));
       compute(g0, mcur, 2);
       fence_async_smem(); mbar_arrive(bar_full + 16);
-      // kb 3 (buffer 1); prefetch kb 0 of the next tile
+      // kb 3 (buffer 1); stage the next tile's metadata (its load has had three K blocks to land), prefetch its kb 0
+      if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
+      __syncwarp();
       if (has_next) issue(g0, mnext, aon, 0);
-      mbar_wait(bar_bfull + 24, par);
+      TWAIT(tw0, mbar_wait<100>(bar_bfull + 24, par));
       compute(g1, mcur, 3);
       fence_async_smem(); mbar_arrive(bar_full + 24);
     }
+    if (EWS_TIMING && warp == 0 && lane == 0) { atomicAdd(p.timing + 0, tw0); atomicAdd(p.timing + 1, (unsigned long long)(clock64() - tstart)); }
   } else if (warp >= NPROD + NEPI) {
     // =================================== MMA ISSUER + B_j LOADERS ======================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
@@ -335,14 +363,15 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       if (lane == 0) {
         const uint64_t dW = make_desc(sbase + OFF_W);
         const uint64_t dS = make_desc(sbase + OFF_S);
+        unsigned long long tw0 = 0, tw1 = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        for (int tile = t_begin; tile < t_end; ++tile, ++it) {
           const int buf = it & 1;
-          if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));   // epilogue drained this buffer
+          if (it >= 2) TWAIT(tw1, mbar_wait<0>(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1)));   // epilogue drained this buffer
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
 #pragma unroll 1
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(bar_full + 8 * kb, (uint32_t)(it & 1));
+            TWAIT(tw0, mbar_wait<0>(bar_full + 8 * kb, (uint32_t)(it & 1)));
             tc_fence_after();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -354,6 +383,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
           }
           mma_commit(bar_accf + 8 * buf);
         }
+        if (EWS_TIMING) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, tw1); }
       }
     } else if (warp <= NPROD + NEPI + 2) {
       // Loader warp lw (0/1) copies the B_j rows of K blocks lw and lw+2 of every tile straight into the S tile with
@@ -367,35 +397,38 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         const int r = lane + 32 * i;
         const int node = tile * 2 + (r >> 6);
         int j = 0;
-        if (tile < p.ntiles && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
+        if (tile < t_end && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
         return j;
       };
       // row r = lane + 32 i sits at ring index (r & 3) * 32 + (r >> 2)
       const uint32_t jput = (uint32_t)((lane & 3) * 32 + (lane >> 2)) * 4u;
-      if ((int)blockIdx.x < p.ntiles) {
+      if (t_begin < t_end) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(blockIdx.x, i));
+        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(t_begin, i));
       }
       __syncwarp();
       // destination of this lane's chunk in row rsub + 4 i: (rsub + 4 i) * 128 + ((c8 ^ ((rsub + 4 i) & 7)) << 4);
       // (rsub + 4 i) & 7 alternates between rsub and rsub + 4 -> two swizzled chunk offsets
       const uint32_t dsw0 = (uint32_t)((c8 ^ rsub) << 4), dsw1 = (uint32_t)((c8 ^ (rsub + 4)) << 4);
       const char* srcb = reinterpret_cast<const char*>(p.Bm) + c8 * 16;
+      unsigned long long tw0 = 0;
+      const long long tstart = clock64();
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u + (uint32_t)rsub * 128u;
         int jn[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) jn[i] = load_j(tile + (int)gridDim.x, i);
+        for (int i = 0; i < 4; ++i) jn[i] = load_j(tile + 1, i);
 #pragma unroll 1
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = lw + 2 * kk;
-          if (it > 0) mbar_wait(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1));
+          if (it > 0) TWAIT(tw0, mbar_wait<100>(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1)));
           const char* src0 = srcb + kb * 128;
           const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)rsub * 128u;
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const uint4 j4 = lds128(jc + (uint32_t)i4 * 16u);
+            uint4 j4 = lds128(jc + (uint32_t)i4 * 16u);
+            if (EWS_EXP & 1) j4 = make_uint4(0, 0, 0, 0);
             const uint32_t d = dst0 + (uint32_t)i4 * 2048u;      // rows rsub + 16 i4 + {0, 4, 8, 12}
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + dsw0), "l"(src0 + (size_t)j4.x * 512) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u + dsw1), "l"(src0 + (size_t)j4.y * 512) : "memory");
@@ -409,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         for (int i = 0; i < 4; ++i) sts32(jnx + (uint32_t)i * 32u, (uint32_t)jn[i]);
         __syncwarp();
       }
+      if (EWS_TIMING && lw == 0 && lane == 0) { atomicAdd(p.timing + 2, tw0); atomicAdd(p.timing + 3, (unsigned long long)(clock64() - tstart)); }
     }
     __syncwarp();
   } else {
@@ -423,13 +457,16 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     const int ecol = ((ch * 2 + (q & 1)) * 32 + lane) * 2;   // first of the 2 columns this thread writes in the final combine
     const float ba = p.ba[0];
     const uint32_t vec_s = sbase + OFF_VEC + (uint32_t)ch * 256u;
+    const uint32_t vec32_s = sbase + OFF_VEC32 + (uint32_t)ch * 512u;
     const uint32_t part_s = sbase + OFF_PART + (uint32_t)erow * 4u;
+    unsigned long long tw0 = 0;
+    const long long tstart = clock64();
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int buf = it & 1;
       const int node = tile * 2 + hn, k = erow & 63;
       const bool valid = node < p.total_nodes && k < p.K;
-      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+      TWAIT(tw0, mbar_wait<200>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
       uint32_t m[64];
@@ -439,6 +476,30 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         uint32_t acc[16];
         tmem_ld16_issue(taddr + c * 16, acc);
         tmem_ld_wait();
+        if (EWS_EPI_FP32) {
+          float dl = 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 bb = lds128(vec32_s + (uint32_t)(c * 16 + g * 4) * 4u);
+            const uint4 ww = lds128(vec32_s + 1024u + (uint32_t)(c * 16 + g * 4) * 4u);
+            float hh[4], mm[4];
+            hh[0] = __uint_as_float(acc[g * 4 + 0]) + __uint_as_float(bb.x);
+            hh[1] = __uint_as_float(acc[g * 4 + 1]) + __uint_as_float(bb.y);
+            hh[2] = __uint_as_float(acc[g * 4 + 2]) + __uint_as_float(bb.z);
+            hh[3] = __uint_as_float(acc[g * 4 + 3]) + __uint_as_float(bb.w);
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hh[e2]));
+              mm[e2] = fmaf(hh[e2], t, hh[e2]);
+            }
+            dl = fmaf(mm[0], __uint_as_float(ww.x), dl); dl = fmaf(mm[1], __uint_as_float(ww.y), dl);
+            dl = fmaf(mm[2], __uint_as_float(ww.z), dl); dl = fmaf(mm[3], __uint_as_float(ww.w), dl);
+            m[c * 8 + g * 2 + 0] = f2h2(mm[0], mm[1]);
+            m[c * 8 + g * 2 + 1] = f2h2(mm[2], mm[3]);
+          }
+          dot += dl;
+        } else {
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -453,6 +514,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         }
         const float2 f0 = h2f2(d0), f1 = h2f2(d1), f2 = h2f2(d2), f3 = h2f2(d3);
         dot += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
@@ -485,6 +547,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
       }
     }
+    if (EWS_TIMING && e == 0 && lane == 0) { atomicAdd(p.timing + 6, tw0); atomicAdd(p.timing + 7, (unsigned long long)(clock64() - tstart)); }
   }
   tc_fence_before();
   __syncthreads();
@@ -509,13 +572,30 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
   p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
   p.agg16 = agg16; p.mstar = a.mstar;
+#if EWS_TIMING
+  static unsigned long long* tbuf = nullptr;
+  if (!tbuf) { CUDA_TRY(cudaMalloc(&tbuf, 64)); CUDA_TRY(cudaMemset(tbuf, 0, 64)); }
+  p.timing = tbuf;
+  {
+    static int calls = 0;
+    if (++calls % 24 == 0) {
+      unsigned long long hbuf[8];
+      cudaMemcpy(hbuf, tbuf, 64, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[ews timing, sums over CTAs, Mcycles] prod wait bfull %.1f of %.1f | loader wait empty %.1f of %.1f | mma wait full %.1f acce %.1f | epi wait accf %.1f of %.1f\n",
+              hbuf[0] * 1e-6, hbuf[1] * 1e-6, hbuf[2] * 1e-6, hbuf[3] * 1e-6, hbuf[4] * 1e-6, hbuf[5] * 1e-6, hbuf[6] * 1e-6, hbuf[7] * 1e-6);
+      cudaMemset(tbuf, 0, 64);
+    }
+  }
+#endif
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
     attr = true;
   }
-  const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
+  int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;
+  p.chunk = (p.ntiles + grid - 1) / grid;
+  grid = (p.ntiles + p.chunk - 1) / p.chunk;
   ews::k_edge_ws<<<grid, ews::NT, ews::SMEM_ALLOC, s>>>(p);
   LAUNCH_CHECK(ctx);
   return 0;
