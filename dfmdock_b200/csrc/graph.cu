@@ -10,6 +10,7 @@
 // residue get their five bin indices, packed into one uint32.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -264,10 +265,186 @@ k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ p
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_graph_sel: same result as k_graph (as sets), selection by bit-wise search instead of k argmin passes.
+// One warp per (trajectory, residue) row; the lane holds the keys of residues j = lane + 32 s in registers as
+// order-preserving unsigned bit patterns of non-negative floats.  The k-th smallest key is found most-significant
+// bit first (one compare per element and one REDUX per bit, starting below the common prefix of all keys), ties at
+// the threshold go to the smaller residue index (like k_graph); members are compacted to slots with warp ballots.
+template <int WARPS, int S>
+__global__ void __launch_bounds__(WARPS * 32)
+k_graph_sel(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ pos, const float* __restrict__ cb,
+            const float* __restrict__ exp_noise, uint64_t seed, uint64_t stream_base, uint32_t fwd,
+            int32_t* __restrict__ nbr, uint32_t* __restrict__ feat, float* __restrict__ radial, int4* __restrict__ emeta) {
+  __shared__ float s_e[WARPS][S * 32];        // Exp(1) draws in residue order (Philox blocks cover 4 residues each)
+  __shared__ int s_slot[WARPS][SLOTS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * WARPS + warp;
+  if (row >= (long)B * N) return;
+  const int b = (int)(row / N), i = (int)(row % N);
+  const size_t gbase = (size_t)b * N;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // ---- distances (float bits; absent -> 0xFFFFFFFF)
+  uint32_t kd[S];
+  {
+    const float* pi = pos + (gbase + i) * 9;
+    const float xi = pi[3], yi = pi[4], zi = pi[5];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int j = lane + 32 * s;
+      kd[s] = 0xFFFFFFFFu;
+      if (j < N) {
+        const float* pj = pos + (gbase + j) * 9;
+        const float dx = xi - pj[3], dy = yi - pj[4], dz = zi - pj[5];
+        kd[s] = __float_as_uint(sqrtf(dx * dx + dy * dy + dz * dz));
+      }
+    }
+  }
+  // k-th smallest of the present keys, then membership flags with ties to the smaller index
+  auto select = [&](const uint32_t (&key)[S], int k, uint32_t& member) {
+    // common prefix: skip the bits on which min and max agree
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (key[s] != 0xFFFFFFFFu) { mn = min(mn, key[s]); mx = max(mx, key[s]); }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    uint32_t v = mn;
+    bool exact = false;            // true: {key < v} has exactly k members
+    if (mn != mx) {
+      const int top = 31 - __clz(mn ^ mx);            // highest differing bit
+      v = (top == 31) ? 0u : (mn >> (top + 1)) << (top + 1);
+      for (int bit = top; bit >= 0; --bit) {
+        const uint32_t test = v | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) cnt += (key[s] < test) ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt == k) { v = test; exact = true; break; }
+        if (cnt < k) v = test;
+      }
+    }
+    member = 0u;                    // bit s: element s of this lane is selected
+    if (exact) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) member |= (key[s] < v) ? (1u << s) : 0u;
+    } else {
+      int less = 0;
+#pragma unroll
+      for (int s = 0; s < S; ++s) less += (key[s] < v) ? 1 : 0;
+      less = __reduce_add_sync(0xffffffffu, less);
+      int need = k - less;          // how many of the keys equal to v to take, smallest index first
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const bool eq = key[s] == v && key[s] != 0xFFFFFFFFu;
+        const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+        const bool take = eq && (int)__popc(bal & lt_mask) < need;
+        member |= ((key[s] < v) || take) ? (1u << s) : 0u;
+        need -= min(need, (int)__popc(bal));
+      }
+    }
+  };
+
+  uint32_t mem1;
+  select(kd, knn, mem1);
+  // slots of the kNN members (index order) and, for injected noise, the rank of every residue among the non-members
+  int base = 0;
+  int nonmember_before[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const bool m = (mem1 >> s) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+    const int below = base + (int)__popc(bal & lt_mask);      // members with a smaller index
+    if (m) s_slot[warp][below] = lane + 32 * s;
+    nonmember_before[s] = (lane + 32 * s) - below;            // compacted column of this residue in the noise row
+    base += (int)__popc(bal);
+  }
+  // ---- exponential race over the remaining residues: key = Exp(1) * d^3, keep the ns smallest
+  if (ns > 0) {
+    if (exp_noise == nullptr) {
+      const uint64_t strm = stream_base + (uint64_t)b;
+      for (int q = lane; q * 4 < N; q += 32) {               // Philox block q covers residues 4q .. 4q+3
+        const uint4 r4 = dfm_rng(seed, strm, RNG_EDGE, fwd, (uint32_t)q, (uint32_t)i);
+        *reinterpret_cast<float4*>(&s_e[warp][q * 4]) =
+            make_float4(-logf(u01_open(r4.x)), -logf(u01_open(r4.y)), -logf(u01_open(r4.z)), -logf(u01_open(r4.w)));
+      }
+      __syncwarp();
+    }
+    uint32_t k2[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int j = lane + 32 * s;
+      k2[s] = 0xFFFFFFFFu;
+      if (j < N && !((mem1 >> s) & 1u)) {
+        const float e = exp_noise ? exp_noise[(gbase + i) * (size_t)(N - knn) + nonmember_before[s]] : s_e[warp][j];
+        const float d = fmaxf(__uint_as_float(kd[s]), 1e-10f);
+        k2[s] = min(__float_as_uint(e * (d * d * d)), 0xFFFFFFFEu);
+      }
+    }
+    uint32_t mem2;
+    select(k2, ns, mem2);
+    int base2 = knn;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool m = (mem2 >> s) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, m);
+      if (m) s_slot[warp][base2 + (int)__popc(bal & lt_mask)] = lane + 32 * s;
+      base2 += (int)__popc(bal);
+    }
+  }
+  __syncwarp();
+  // ---- pair features for the K selected edges; pad slots point at the residue itself
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int k = lane + 32 * half;
+    int j = i;
+    uint32_t ft = 0;
+    float r2 = 0.f;
+    if (k < K) {
+      j = min(max(s_slot[warp][k], 0), N - 1);
+      ft = pair_bins(pos, cb, (int)(gbase + i), (int)(gbase + j), i, j, R, &r2);
+    }
+    const size_t o = (gbase + i) * SLOTS + k;
+    nbr[o] = j;
+    feat[o] = ft;
+    radial[o] = r2;
+    {
+      const uint32_t otp = (ft >> 6) & 0x3FFFu;
+      const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
+      const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
+      const __half2 rh = __float2half2_rn(fminf(r2 * 0.03125f, 65000.f));
+      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, *reinterpret_cast<const int*>(&rh));
+    }
+  }
+}
+
+template <int S>
+static int launch_graph_sel(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
+                            uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
+  constexpr int WARPS = 8;
+  const long rows = (long)B * ctx->N;
+  const int grid = (int)((rows + WARPS - 1) / WARPS);
+  k_graph_sel<WARPS, S><<<grid, WARPS * 32, 0, s>>>(B, ctx->N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, exp_noise,
+                                                   seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
                  uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
   constexpr int WARPS = 8;
   const int N = ctx->N;
+  // register-resident selection for the common sizes (no injected edge table); larger complexes use the smem kernel
+  static int use_sel = -1;
+  if (use_sel < 0) { const char* e = getenv("DFM_GRAPH_KERNEL"); use_sel = e ? atoi(e) : 1; }
+  if (use_sel && edges == nullptr && N >= 2) {
+    if (N <= 320) return launch_graph_sel<10>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
+    if (N <= 512) return launch_graph_sel<16>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
+    if (N <= 1024) return launch_graph_sel<32>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
+  }
   const int npad = (N + 31) & ~31;
   const size_t smem = (size_t)WARPS * (npad + 32) * sizeof(float);
   if (smem > 200 * 1024) {
