@@ -105,8 +105,8 @@ def cpu_reference_throughput(num_traj, num_steps, threads=None):
     """The reference's algorithm on the host cores: oracle port, serial trajectories at batch 1 like the reference."""
     import torch
     from oracle import dfmdock_oracle as orc
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     sd, hp, batch = make_workload()
     net = orc.OracleNet(sd, cut_off=hp["model"]["cut_off"])
     import numpy as np

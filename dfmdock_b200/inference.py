@@ -1,0 +1,227 @@
+"""Entry points of the docking sampler, mirroring the reference's CLI surface on top of the CUDA library.
+
+Reference entry points mirrored:
+    src/inference.py:569-596           argparse surface (--paths | --csv, --ckpt, --out_dir, --out_csv_dir, --out_csv,
+                                       --num_samples, --num_steps, --tr_noise_scale, --rot_noise_scale,
+                                       --use_clash_force, --noise_annealing, --seed)
+    src/inference.py:375-413, 418-495  run(args, model, inputs, batch, device) / main(args): per-sample rows of the
+                                       metrics CSV (id, index, ..., energy, num_clashes), one structure file per sample
+    src/inference.py:500-567           inference(in_1, in_2): pinder_0.ckpt, 40 samples x 40 steps, clash force,
+                                       all-atom-centroid rotation convention, keep the lowest-energy pose -> output.pdb
+    src/inference_base.py:601-670      inference(in_1, in_2): dips ckpt, 120 x 40, CA-centroid convention (variant="base")
+    src/inference_single.py:1-12       `python -m dfmdock_b200.inference_single a b`
+
+What differs, and why:
+  * inputs are the reference's own pre-embedded records (data/db5_test/<id>.pt: backbone + ESM-2 embeddings + sequence);
+    parsing raw PDB files and running ESM-2 (src/inference_base.py:72-306; needs biotite + fair-esm, both absent here)
+    is the "next" row of SURVEY.md 8(f).  A `.pdb` argument raises NotImplementedError saying so -- nothing is faked.
+  * all trajectories of a complex advance in lock step on the GPU (sample_trajectories) instead of the reference's
+    serial loop; `--reference_rng` restores the serial loop with the reference's RNG consumption order.
+  * structures are written as backbone-only PDB (N, CA, C of both chains); the all-atom rigid transform + biotite
+    writer is out of scope, but rot_update / tr_update (what modify_aa_coords consumes) are stored in the CSV.
+  * `confidence_logits` (src/inference.py:397) does not exist in the reference's own network output.
+"""
+import argparse
+import csv
+import os
+import random
+
+import numpy as np
+import torch
+
+from .checkpoint import load_db5_record
+from .features import batch_from_record
+from .sampler import Euler_Maruyama_sampler, sample_trajectories
+from .score_model import Score_Model
+
+THREE = {"A": "ALA", "R": "ARG", "N": "ASN", "D": "ASP", "C": "CYS", "Q": "GLN", "E": "GLU", "G": "GLY", "H": "HIS",
+         "I": "ILE", "L": "LEU", "K": "LYS", "M": "MET", "F": "PHE", "P": "PRO", "S": "SER", "T": "THR", "W": "TRP",
+         "Y": "TYR", "V": "VAL"}
+
+
+def set_seed(seed):
+    """src/inference_base.py:24-32"""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def load_inputs(path_1, path_2=None, id=None):
+    """-> inputs dict {"id", "receptor": {x, pos, seq}, "ligand": {...}}.
+
+    path_1 alone: a two-chain record (data/db5_test/<id>.pt layout).  path_1 + path_2: one single-chain record each
+    ({"x", "pos", "seq"}).  Raw PDB files need the ESM-2 front end, which is not part of this path.
+    """
+    for p in (path_1, path_2):
+        if p is not None and str(p).lower().endswith((".pdb", ".ent", ".cif")):
+            raise NotImplementedError(
+                "%s: raw structure files need the PDB parser + ESM-2 650M embedding front end of the reference "
+                "(src/inference_base.py:72-306; biotite and fair-esm are not available here).  Pass the reference's "
+                "pre-embedded record (.pt with x / pos / seq per chain) instead." % p)
+    if path_2 is None or path_2 == path_1:
+        rec = load_db5_record(path_1)
+    else:
+        a = torch.load(path_1, map_location="cpu", weights_only=False)
+        b = torch.load(path_2, map_location="cpu", weights_only=False)
+        rec = {"receptor": a.get("receptor", a), "ligand": b.get("ligand", b)}
+    rec["id"] = id or rec.get("name") or os.path.splitext(os.path.basename(str(path_1)))[0]
+    return rec
+
+
+def write_backbone_pdb(path, rec_pos, lig_pos, rec_seq, lig_seq):
+    """Backbone-only PDB (chain A = receptor, chain B = ligand; atoms N, CA, C)."""
+    lines = []
+    serial = 1
+    for chain, pos, seq in (("A", rec_pos, rec_seq), ("B", lig_pos, lig_seq)):
+        pos = torch.as_tensor(pos).detach().cpu().double()
+        for r in range(pos.shape[0]):
+            res = THREE.get(seq[r] if r < len(seq) else "X", "UNK")
+            for a, name in enumerate(("N", "CA", "C")):
+                x, y, z = (float(v) for v in pos[r, a])
+                lines.append("ATOM  %5d  %-3s %3s %1s%4d    %8.3f%8.3f%8.3f  1.00  0.00           %1s" %
+                             (serial % 100000, name, res, chain, (r + 1) % 10000, x, y, z, name[0]))
+                serial += 1
+        lines.append("TER")
+    lines.append("END")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def _rmsd(a, b):
+    return float(((a - b) ** 2).sum(-1).mean().sqrt())
+
+
+def ligand_rmsd(lig_pos, native_lig_pos):
+    """CA RMSD of the docked ligand to its pose in the input record with the receptor frame fixed (the receptor never
+    moves in the sampler).  The full metric set (Kabsch C/I-RMSD, Fnat, DockQ: src/utils/metrics.py) is a 'next' row."""
+    return _rmsd(torch.as_tensor(lig_pos)[:, 1].double().cpu(), torch.as_tensor(native_lig_pos)[:, 1].double().cpu())
+
+
+def run(args, model, inputs, batch, device):
+    """Per-sample metric rows + one structure file per sample (src/inference.py:375-413)."""
+    centre_mode = int(getattr(args, "centre_mode", 1))
+    rows = []
+    native_lig = batch["lig_pos"].clone()
+    if getattr(args, "reference_rng", False):
+        poses = []
+        for i in range(args.num_samples):
+            rec_pos, lig_pos, rot_update, tr_update, output = Euler_Maruyama_sampler(
+                model=model, batch=dict(batch), num_steps=args.num_steps, device=device,
+                use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing,
+                tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode)
+            poses.append((lig_pos.cpu(), rot_update.view(3).cpu(), tr_update.view(3).cpu(), float(output["energy"]),
+                          int(output["num_clashes"])))
+    else:
+        res = sample_trajectories(model, batch, args.num_samples, num_steps=args.num_steps,
+                                  use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing,
+                                  tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale,
+                                  centre_mode=centre_mode, seed=args.seed, gather_poses=True)
+        poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
+                  int(res["num_clashes"][i])) for i in range(args.num_samples)]
+    rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+    for i, (lig_pos, rot_u, tr_u, energy, clashes) in enumerate(poses):
+        rows.append({"id": inputs["id"], "index": str(i), "l_rmsd": ligand_rmsd(lig_pos, native_lig), "energy": energy,
+                     "num_clashes": clashes, "rot_update": " ".join("%.6f" % float(v) for v in rot_u),
+                     "tr_update": " ".join("%.6f" % float(v) for v in tr_u)})
+        if rank == 0 and getattr(args, "out_dir", None):
+            write_backbone_pdb(os.path.join(args.out_dir, "%s_%d.pdb" % (inputs["id"], i)), batch["rec_pos"], lig_pos,
+                               inputs["receptor"]["seq"], inputs["ligand"]["seq"])
+    return rows
+
+
+def main(args):
+    """src/inference.py:418-495"""
+    paths_list = []
+    if args.paths:
+        id, p1, p2 = args.paths
+        if os.path.exists(p1) and os.path.exists(p2):
+            paths_list.append((id, p1, p2))
+        else:
+            print("One or both paths do not exist.")
+    elif args.csv:
+        if os.path.exists(args.csv):
+            with open(args.csv, "r") as f:
+                for row in csv.reader(f):
+                    paths_list.append((row[0], row[1], row[2] if len(row) > 2 else row[1]))
+        else:
+            print("CSV file does not exist.")
+    os.makedirs(args.out_dir, exist_ok=True)
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if device is None:
+        raise RuntimeError("dfmdock_b200.inference needs a CUDA (sm_100a) device; there is no CPU path")
+    model = Score_Model.load_from_checkpoint(args.ckpt, map_location=device)
+    model.to(device).eval()
+    results = []
+    for id, p1, p2 in paths_list:
+        inputs = load_inputs(p1, p2, id=id)
+        batch = batch_from_record(inputs, pos_width=model.pos_width)
+        results.extend(run(args, model, inputs, batch, device))
+    os.makedirs(args.out_csv_dir, exist_ok=True)
+    out = os.path.join(args.out_csv_dir, args.out_csv)
+    if results:
+        with open(out, "w", newline="") as f:
+            w = csv.DictWriter(f, fieldnames=list(results[0].keys()))
+            w.writeheader()
+            for row in results:
+                w.writerow(row)
+    return results
+
+
+def inference(in_1, in_2=None, ckpt=None, variant="pinder", num_samples=None, num_steps=40, out="output.pdb", seed=None):
+    """Dock one complex and write the lowest-energy pose (src/inference.py:500-567; variant="base":
+    src/inference_base.py:601-670).  Returns {"energy", "rot_update", "tr_update", "lig_pos", "index"}."""
+    if variant == "pinder":
+        ckpt = ckpt or "./weights/pinder_0.ckpt"
+        num_samples = num_samples or 40
+        use_clash_force, centre_mode = True, 1
+    else:
+        ckpt = ckpt or "./checkpoints/dips/model_0.ckpt"
+        num_samples = num_samples or 120
+        use_clash_force, centre_mode = False, 0
+    if not torch.cuda.is_available():
+        raise RuntimeError("dfmdock_b200.inference needs a CUDA (sm_100a) device; there is no CPU path")
+    device = torch.device("cuda", torch.cuda.current_device())
+    model = Score_Model.load_from_checkpoint(ckpt, map_location=device)
+    model.to(device).eval()
+    inputs = load_inputs(in_1, in_2)
+    batch = batch_from_record(inputs, pos_width=model.pos_width)
+    res = sample_trajectories(model, batch, num_samples, num_steps=num_steps, use_clash_force=use_clash_force,
+                              centre_mode=centre_mode, seed=0 if seed is None else seed, gather_poses=True)
+    best = res["best"]
+    lig = res["lig_pos"][best].cpu()
+    if out:
+        write_backbone_pdb(out, batch["rec_pos"], lig, inputs["receptor"]["seq"], inputs["ligand"]["seq"])
+    return {"energy": float(res["energy"][best]), "rot_update": res["rot_update"][best].cpu(),
+            "tr_update": res["tr_update"][best].cpu(), "lig_pos": lig, "index": best}
+
+
+def build_parser():
+    """Same flags as src/inference.py:569-589 (+ --reference_rng, --centre_mode)."""
+    parser = argparse.ArgumentParser(description="DFMDock reverse-diffusion docking sampler (B200 CUDA path)")
+    group = parser.add_mutually_exclusive_group(required=True)
+    group.add_argument("--paths", nargs=3, metavar=("id", "in_1", "in_2"), help="id and two input records")
+    group.add_argument("--csv", type=str, help="CSV file with rows: id, in_1, in_2")
+    parser.add_argument("--ckpt", type=str, default="../checkpoints/dips/model_0.ckpt")
+    parser.add_argument("--out_dir", type=str, default="./pdbs")
+    parser.add_argument("--out_csv_dir", type=str, default="./csv_files")
+    parser.add_argument("--out_csv", type=str, default="./test.csv")
+    parser.add_argument("--num_samples", type=int, default=1)
+    parser.add_argument("--num_steps", type=int, default=40)
+    parser.add_argument("--tr_noise_scale", type=float, default=0.5)
+    parser.add_argument("--rot_noise_scale", type=float, default=0.5)   # the reference declares type=int here (App. D.5)
+    parser.add_argument("--use_clash_force", action="store_true")
+    parser.add_argument("--noise_annealing", action="store_true")
+    parser.add_argument("--seed", type=int, default=42)
+    parser.add_argument("--reference_rng", action="store_true",
+                        help="serial trajectories with the reference's RNG consumption order instead of batched Philox")
+    parser.add_argument("--centre_mode", type=int, default=1, choices=[0, 1],
+                        help="1: rotate about the N/CA/C centroid (src/inference.py), 0: CA centroid (src/inference_base.py)")
+    return parser
+
+
+if __name__ == "__main__":
+    _args = build_parser().parse_args()
+    set_seed(_args.seed)
+    main(_args)

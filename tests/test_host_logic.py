@@ -146,3 +146,33 @@ def test_bench_roofline_arithmetic():
     for n, gf in ((197, 11.66), (300, 17.76), (800, 47.36)):
         assert abs(bench.algorithmic_flops_per_pose_step(n) / 1e9 - gf) < 0.02
     assert bench.edge_kernel_flops_per_launch(256, 300) == 2 * 4608000 * 65536 + 2 * 4608000 * 256
+
+
+def test_inference_cli_surface_matches_reference_flags(tmp_path):
+    """src/inference.py:569-589: same flag names / defaults; raw PDB inputs are refused loudly (ESM front end is out of scope)."""
+    from dfmdock_b200 import inference as inf
+    p = inf.build_parser()
+    a = p.parse_args(["--paths", "x", "a.pt", "b.pt"])
+    assert (a.num_samples, a.num_steps, a.tr_noise_scale, a.rot_noise_scale, a.seed) == (1, 40, 0.5, 0.5, 42)
+    assert a.ckpt == "../checkpoints/dips/model_0.ckpt" and a.out_dir == "./pdbs" and a.out_csv == "./test.csv"
+    assert not a.use_clash_force and not a.noise_annealing
+    with pytest.raises(SystemExit):
+        p.parse_args([])                       # --paths | --csv is required, like the reference
+    with pytest.raises(NotImplementedError):
+        inf.load_inputs("1A2K_r_b.pdb", "1A2K_l_b.pdb")
+    # record loading + backbone writer
+    from dfmdock_b200.features import synthetic_complex
+    b = synthetic_complex(6, 5, seed=1)
+    rec = {"receptor": {"x": b["rec_x"][:, :1280], "pos": b["rec_pos"], "seq": "ACDEFG"},
+           "ligand": {"x": b["lig_x"][:, :1280], "pos": b["lig_pos"], "seq": "HIKLM"}}
+    path = tmp_path / "cplx.pt"
+    torch.save(rec, path)
+    got = inf.load_inputs(str(path), id="cplx")
+    assert got["id"] == "cplx" and got["ligand"]["seq"] == "HIKLM"
+    out = tmp_path / "o.pdb"
+    inf.write_backbone_pdb(str(out), b["rec_pos"], b["lig_pos"], "ACDEFG", "HIKLM")
+    lines = out.read_text().splitlines()
+    assert sum(l.startswith("ATOM") for l in lines) == 33 and lines[-1] == "END"
+    assert lines[0][12:16].strip() == "N" and lines[0][17:20] == "ALA" and lines[0][21] == "A"
+    assert abs(float(lines[1][30:38]) - float(b["rec_pos"][0, 1, 0])) < 1e-3
+    assert inf.ligand_rmsd(b["lig_pos"], b["lig_pos"]) == 0.0
