@@ -434,37 +434,8 @@ int launch_image_pack_z(dfm_ctx* ctx, const float* W3, float scale_hi, __half* i
   return 0;
 }
 
-// Ah = fp16((W1s h + b1eff)/2) and Bm = fp16((W1d h)/2) in one launch (two halves of the grid)
-int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s) {
-  const LayerW& w = ctx->layer[layer];
-  ntc::Params p{};
-  p.M = M; p.ntiles = (M + ntc::TILE_M - 1) / ntc::TILE_M; p.N = ctx->N;
-  p.X = h16; p.W0 = w.img_W1s; p.W1 = w.img_W1d; p.bias0 = w.b1eff; p.out0 = Ah; p.out1 = Bm;
-  int half = ctx->num_sms / 2;
-  if (half > p.ntiles) half = p.ntiles;
-  return ntc::launch<ntc::MODE_AB>(ctx, p, 2 * half, s);
-}
-
-// z = W3h h + W3a agg + b3 (agg16 carries agg x 2^-6, the image carries W3a x 2^6)
-int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s) {
-  const LayerW& w = ctx->layer[layer];
-  ntc::Params p{};
-  p.M = M; p.ntiles = (M + ntc::TILE_M - 1) / ntc::TILE_M; p.N = ctx->N;
-  p.X = h16; p.X2 = agg16; p.W0 = w.img_W3z0; p.W1 = w.img_W3z1; p.bias0 = w.b3; p.out32 = z;
-  int half = ctx->num_sms / 2;
-  if (half > p.ntiles) half = p.ntiles;
-  return ntc::launch<ntc::MODE_Z>(ctx, p, 2 * half, s);
-}
-
-// h += W4 SiLU(z * gscale + gshift) + b4; h16 = fp16(h)
-int launch_node_h(dfm_ctx* ctx, int layer, int M, const float* z, const float* gscale, const float* gshift, float* h,
-                  __half* h16, cudaStream_t s) {
-  const LayerW& w = ctx->layer[layer];
-  ntc::Params p{};
-  p.M = M; p.ntiles = (M + ntc::TILE_M - 1) / ntc::TILE_M; p.N = ctx->N;
-  p.W0 = w.img_W4; p.bias0 = w.b4; p.z = z; p.gscale = gscale; p.gshift = gshift; p.h = h; p.h16 = h16;
-  return ntc::launch<ntc::MODE_H>(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
-}
+// MODE_AB / MODE_Z / MODE_H are launched from node_t.cu (transposed formulation, coalesced epilogue); this file's
+// instantiation that is used on the hot path is MODE_C.
 
 // per-residue force of the ligand (last layer): replaces tc.cu k_tc<COORD> on the throughput path
 int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
