@@ -40,6 +40,9 @@ PROTOTYPES = {
     "dfm_profile_enable": (c_int, [c_void_p, c_int]),
     "dfm_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int)]),
     "dfm_debug_read": (c_int64, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dfm_metrics_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dfm_compute_metrics": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
     "dfm_last_error": (c_char_p, []),
     "dfm_version": (c_char_p, []),
     "dfm_destroy": (None, [c_void_p]),

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdfmdock_b200.so")
-SOURCES = ["api.cu", "graph.cu", "simt.cu", "tc.cu", "edge_ws.cu", "node_tc.cu", "node_t.cu", "node.cu", "pose.cu"]
+SOURCES = ["api.cu", "graph.cu", "simt.cu", "tc.cu", "edge_ws.cu", "node_tc.cu", "node_t.cu", "node.cu", "pose.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

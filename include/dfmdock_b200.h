@@ -154,6 +154,19 @@ int dfm_profile_read(dfm_ctx* ctx, double* edge_kernel_ms, int* launches);
  * 6 = per-residue force [B,L,4].  Returns the element count or a negative error. */
 int64_t dfm_debug_read(dfm_ctx* ctx, int B, int which, void* out, size_t out_bytes, void* workspace, void* stream);
 
+/* ---- the consumer of the sampler's output ------------------------------------------------
+ * Replaces: compute_metrics (src/utils/metrics.py:3-16: get_c_rmsd :33-38, get_i_rmsd :40-46, get_l_rmsd :48-56,
+ * get_fnat :58-69, get_DockQ :71-74, find_rigid_alignment :91-121) for T docked poses of one complex, batched.
+ *   model_rec  [R,3,3] when rec_is_shared != 0 (the sampler never moves the receptor) else [T,R,3,3]
+ *   model_lig  [T,L,3,3];  native_rec [R,3,3];  native_lig [L,3,3]   (backbone N, CA, C; Angstrom; DEVICE pointers)
+ *   out        [T,5] = c_rmsd, i_rmsd, l_rmsd, fnat, DockQ  (i_rmsd / DockQ are NaN when the native has no interface)
+ *   workspace  dfm_metrics_workspace_bytes(R, L) bytes of device scratch
+ * Needs no context; stream-ordered on `stream`; returns 0 or a negative DFM_E* code. */
+size_t dfm_metrics_workspace_bytes(int R, int L);
+int dfm_compute_metrics(int device, int T, int R, int L, const float* model_rec, int rec_is_shared,
+                        const float* model_lig, const float* native_rec, const float* native_lig, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 const char* dfm_last_error(void);
 const char* dfm_version(void);
 void dfm_destroy(dfm_ctx* ctx);
