@@ -8,6 +8,7 @@ plus batched / sharded sampling (sample_trajectories).  All compute is in libdfm
 from .score_model import Score_Model
 from .sampler import Euler_Maruyama_sampler, sample_trajectories
 from .features import batch_from_record, get_position_matrix, synthetic_complex
+from .metrics import compute_metrics, compute_metrics_batch
 
 __all__ = ["Score_Model", "Euler_Maruyama_sampler", "sample_trajectories", "batch_from_record",
-           "get_position_matrix", "synthetic_complex"]
+           "get_position_matrix", "synthetic_complex", "compute_metrics", "compute_metrics_batch"]

@@ -17,6 +17,8 @@ What differs, and why:
     is the "next" row of SURVEY.md 8(f).  A `.pdb` argument raises NotImplementedError saying so -- nothing is faked.
   * all trajectories of a complex advance in lock step on the GPU (sample_trajectories) instead of the reference's
     serial loop; `--reference_rng` restores the serial loop with the reference's RNG consumption order.
+  * the metric columns (c_rmsd, i_rmsd, l_rmsd, fnat, DockQ: src/utils/metrics.py) come from one batched CUDA launch
+    over all poses (dfmdock_b200.metrics) instead of one torch SVD per sample.
   * structures are written as backbone-only PDB (N, CA, C of both chains); the all-atom rigid transform + biotite
     writer is out of scope, but rot_update / tr_update (what modify_aa_coords consumes) are stored in the CSV.
   * `confidence_logits` (src/inference.py:397) does not exist in the reference's own network output.
@@ -31,6 +33,7 @@ import torch
 
 from .checkpoint import load_db5_record
 from .features import batch_from_record
+from .metrics import KEYS as METRIC_KEYS, compute_metrics_batch
 from .sampler import Euler_Maruyama_sampler, sample_trajectories
 from .score_model import Score_Model
 
@@ -95,7 +98,7 @@ def _rmsd(a, b):
 
 def ligand_rmsd(lig_pos, native_lig_pos):
     """CA RMSD of the docked ligand to its pose in the input record with the receptor frame fixed (the receptor never
-    moves in the sampler).  The full metric set (Kabsch C/I-RMSD, Fnat, DockQ: src/utils/metrics.py) is a 'next' row."""
+    moves in the sampler); a quick CA-only figure -- the reference's metric set is dfmdock_b200.metrics."""
     return _rmsd(torch.as_tensor(lig_pos)[:, 1].double().cpu(), torch.as_tensor(native_lig_pos)[:, 1].double().cpu())
 
 
@@ -121,10 +124,16 @@ def run(args, model, inputs, batch, device):
         poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
                   int(res["num_clashes"][i])) for i in range(args.num_samples)]
     rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+    # metrics of every pose in one launch (src/inference.py:393 calls compute_metrics per sample); the native pose is the
+    # one in the input record, like the reference's `native = inputs[...]['bb_coords']`
+    met = compute_metrics_batch(batch["rec_pos"], torch.stack([p[0] for p in poses]), batch["rec_pos"], native_lig,
+                                device=device).cpu()
     for i, (lig_pos, rot_u, tr_u, energy, clashes) in enumerate(poses):
-        rows.append({"id": inputs["id"], "index": str(i), "l_rmsd": ligand_rmsd(lig_pos, native_lig), "energy": energy,
-                     "num_clashes": clashes, "rot_update": " ".join("%.6f" % float(v) for v in rot_u),
-                     "tr_update": " ".join("%.6f" % float(v) for v in tr_u)})
+        row = {"id": inputs["id"], "index": str(i)}
+        row.update({k: (round(float(met[i, j]), 6) if k == "fnat" else float(met[i, j])) for j, k in enumerate(METRIC_KEYS)})
+        row.update({"energy": energy, "num_clashes": clashes, "rot_update": " ".join("%.6f" % float(v) for v in rot_u),
+                    "tr_update": " ".join("%.6f" % float(v) for v in tr_u)})
+        rows.append(row)
         if rank == 0 and getattr(args, "out_dir", None):
             write_backbone_pdb(os.path.join(args.out_dir, "%s_%d.pdb" % (inputs["id"], i)), batch["rec_pos"], lig_pos,
                                inputs["receptor"]["seq"], inputs["ligand"]["seq"])

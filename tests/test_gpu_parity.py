@@ -341,7 +341,10 @@ def test_inference_entry_points_write_csv_and_structures(tmp_path):
     assert all(torch.isfinite(torch.tensor(r["energy"])) for r in rows)
     with open(tmp_path / "csv" / "t.csv") as f:
         got = list(_csv.DictReader(f))
-    assert [g["index"] for g in got] == ["0", "1", "2", "3"] and "num_clashes" in got[0] and "energy" in got[0]
+    assert [g["index"] for g in got] == ["0", "1", "2", "3"]
+    # the reference's CSV schema (src/inference_base.py:494-500), then the rigid transform the all-atom writer needs
+    assert list(got[0].keys())[:9] == ["id", "index", "c_rmsd", "i_rmsd", "l_rmsd", "fnat", "DockQ", "energy", "num_clashes"]
+    assert all(0.0 <= float(g["fnat"]) <= 1.0 and float(g["l_rmsd"]) >= 0.0 for g in got)
     assert sorted(p.name for p in (tmp_path / "pdbs").iterdir()) == ["cplx_%d.pdb" % i for i in range(4)]
     # same seed -> same result (Philox), and the serial reference-RNG path runs through the same kernels
     rows2 = inf.main(args)
