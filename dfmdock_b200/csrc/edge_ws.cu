@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
       uint32_t m[64];
       float dot = 0.f;
+      uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint32_t acc[16];
@@ -500,7 +501,6 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
           }
           dot += dl;
         } else {
-        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint4 bb = lds128(vec_s + (uint32_t)(c * 16 + g * 8) * 2u);
@@ -512,8 +512,11 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
           m[c * 8 + g * 4 + 0] = x0; m[c * 8 + g * 4 + 1] = x1; m[c * 8 + g * 4 + 2] = x2; m[c * 8 + g * 4 + 3] = x3;
           d0 = h2fma(x0, ww.x, d0); d1 = h2fma(x1, ww.y, d1); d2 = h2fma(x2, ww.z, d2); d3 = h2fma(x3, ww.w, d3);
         }
-        const float2 f0 = h2f2(d0), f1 = h2f2(d1), f2 = h2f2(d2), f3 = h2f2(d3);
-        dot += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        if (c & 1) {        // 4 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
+          const float2 f0 = h2f2(h2add(d0, d1)), f1 = h2f2(h2add(d2, d3));
+          dot += (f0.x + f0.y) + (f1.x + f1.y);
+          d0 = d1 = d2 = d3 = 0;
+        }
         }
       }
       tc_fence_before();
