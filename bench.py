@@ -57,13 +57,46 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML every 20 ms (nvidia-smi every 200 ms if NVML
+    cannot be opened)."""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.samples, self.stop, self.source = index, uuid, [], False, "nvidia-smi"
         self.thread = threading.Thread(target=self.run, daemon=True)
 
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode())
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
     def run(self):
+        try:
+            nv, h = self._nvml_handle()
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+            self.source = "nvml"
+            while not self.stop:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.02)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
@@ -76,6 +109,7 @@ class ClockSampler:
 
     def __enter__(self):
         self.thread.start()
+        time.sleep(0.05)       # let the sampler open NVML before the timed region starts
         return self
 
     def __exit__(self, *a):
@@ -91,7 +125,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": self.source}
 
 
 def make_workload():
@@ -189,10 +223,14 @@ def run_cuda(args):
     sync_all()
 
     # ---- device-resident timed region ------------------------------------------------------------
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
     model.profile_enable(args.steps * 8)
     launches0 = model.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, gpu_uuid) as clocks:
         sync_all()
         e0.record()
         for _ in range(args.steps):
