@@ -43,6 +43,7 @@ PROTOTYPES = {
     "dfm_metrics_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dfm_compute_metrics": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
+    "dfm_transform_atoms": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dfm_last_error": (c_char_p, []),
     "dfm_version": (c_char_p, []),
     "dfm_destroy": (None, [c_void_p]),

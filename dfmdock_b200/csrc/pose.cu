@@ -256,3 +256,49 @@ int launch_reverse_step(dfm_ctx* ctx, int B, float* lig_pos, float* rot_update, 
   }
   return 0;
 }
+
+// ---- all-atom rigid transform of the docked ligand -----------------------------------------
+// Restates modify_aa_coords: x <- (x - c) R^T + c + tr with R = axis_angle_to_matrix(rot_update);
+//   centre_mode 0: c = centroid of the ligand's backbone CA atoms      (src/inference_base.py:354-364)
+//   centre_mode 1: c = centroid of the all-atom coordinates themselves (src/inference.py:256-266)
+// One CTA per pose; atoms [A,3] are shared by all poses, out is [T,A,3].
+__global__ void __launch_bounds__(256)
+k_transform_atoms(int A, int L, int centre_mode, const float* __restrict__ atoms, const float* __restrict__ lig_bb,
+                  const float* __restrict__ rot_update, const float* __restrict__ tr_update, float* __restrict__ out) {
+  __shared__ float red[3][8];
+  const int b = blockIdx.x;
+  float cx, cy, cz;
+  if (centre_mode == 0) {
+    centroid(lig_bb, L, 0, cx, cy, cz, red);
+  } else {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int a = threadIdx.x; a < A; a += 256) { sx += atoms[a * 3]; sy += atoms[a * 3 + 1]; sz += atoms[a * 3 + 2]; }
+    block_sum3(sx, sy, sz, red);
+    const float inv = 1.f / (float)A;
+    cx = sx * inv; cy = sy * inv; cz = sz * inv;
+  }
+  const float aa[3] = {rot_update[b * 3], rot_update[b * 3 + 1], rot_update[b * 3 + 2]};
+  const M3 Rm = aa_to_mat(aa);
+  const float tx = tr_update[b * 3] + cx, ty = tr_update[b * 3 + 1] + cy, tz = tr_update[b * 3 + 2] + cz;
+  float* o = out + (size_t)b * A * 3;
+  for (int a = threadIdx.x; a < A; a += 256) {
+    const float x = atoms[a * 3] - cx, y = atoms[a * 3 + 1] - cy, z = atoms[a * 3 + 2] - cz;
+    o[a * 3 + 0] = Rm.m[0] * x + Rm.m[1] * y + Rm.m[2] * z + tx;
+    o[a * 3 + 1] = Rm.m[3] * x + Rm.m[4] * y + Rm.m[5] * z + ty;
+    o[a * 3 + 2] = Rm.m[6] * x + Rm.m[7] * y + Rm.m[8] * z + tz;
+  }
+}
+
+extern "C" int dfm_transform_atoms(int device, int T, int A, int L, int centre_mode, const float* atoms,
+                                   const float* lig_bb, const float* rot_update, const float* tr_update, float* out,
+                                   void* stream) {
+  if (T <= 0 || A <= 0 || !atoms || !rot_update || !tr_update || !out || (centre_mode == 0 && (L <= 0 || !lig_bb)) ||
+      (centre_mode != 0 && centre_mode != 1)) {
+    dfm_set_error("dfm_transform_atoms: bad argument");
+    return DFM_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  k_transform_atoms<<<T, 256, 0, (cudaStream_t)stream>>>(A, L, centre_mode, atoms, lig_bb, rot_update, tr_update, out);
+  if (cudaGetLastError() != cudaSuccess) { dfm_set_error("dfm_transform_atoms: launch failed"); return DFM_ECUDA; }
+  return DFM_OK;
+}

@@ -12,15 +12,21 @@ Reference entry points mirrored:
     src/inference_single.py:1-12       `python -m dfmdock_b200.inference_single a b`
 
 What differs, and why:
-  * inputs are the reference's own pre-embedded records (data/db5_test/<id>.pt: backbone + ESM-2 embeddings + sequence);
-    parsing raw PDB files and running ESM-2 (src/inference_base.py:72-306; needs biotite + fair-esm, both absent here)
-    is the "next" row of SURVEY.md 8(f).  A `.pdb` argument raises NotImplementedError saying so -- nothing is faked.
+  * inputs are either the reference's own pre-embedded records (data/db5_test/<id>.pt: backbone + ESM-2 embeddings +
+    sequence) or raw PDB files.  PDB files go through dfmdock_b200.pdbio (biotite-free get_info_from_pdb) and need ESM-2
+    650M embeddings: `--esm_dir` points at a LOCAL Hugging Face export of esm2_t33_650M_UR50D (fair-esm is absent and
+    there is no network here); without it a `.pdb` argument fails loudly -- nothing is faked.
   * all trajectories of a complex advance in lock step on the GPU (sample_trajectories) instead of the reference's
     serial loop; `--reference_rng` restores the serial loop with the reference's RNG consumption order.
   * the metric columns (c_rmsd, i_rmsd, l_rmsd, fnat, DockQ: src/utils/metrics.py) come from one batched CUDA launch
     over all poses (dfmdock_b200.metrics) instead of one torch SVD per sample.
-  * structures are written as backbone-only PDB (N, CA, C of both chains); the all-atom rigid transform + biotite
-    writer is out of scope, but rot_update / tr_update (what modify_aa_coords consumes) are stored in the CSV.
+  * PDB inputs are written back all-atom: modify_aa_coords for every sample in one launch (dfm_transform_atoms) +
+    combine_atom_arrays + a fixed-column writer (pdbio.write_pdb).  Pre-embedded records carry no side chains, so they are
+    written backbone-only (N, CA, C of both chains); rot_update / tr_update are stored in the CSV either way.
+  * under torchrun (WORLD_SIZE > 1) the trajectories of every complex are sharded over the ranks (one all-gather of the
+    [T,8] result rows per complex); rank 0 writes the files.
+  * extras of the class-form sampler (src/inference_mlsb.py): --ode, --out_trj_dir (multi-MODEL trajectory dumps),
+    --get_gt_energy (score the input pose at t = 1e-5 instead of sampling).
   * `confidence_logits` (src/inference.py:397) does not exist in the reference's own network output.
 """
 import argparse
@@ -31,6 +37,7 @@ import random
 import numpy as np
 import torch
 
+from . import pdbio
 from .checkpoint import load_db5_record
 from .features import batch_from_record
 from .metrics import KEYS as METRIC_KEYS, compute_metrics_batch
@@ -51,18 +58,26 @@ def set_seed(seed):
         torch.cuda.manual_seed_all(seed)
 
 
-def load_inputs(path_1, path_2=None, id=None):
-    """-> inputs dict {"id", "receptor": {x, pos, seq}, "ligand": {...}}.
+STRUCTURE_EXT = (".pdb", ".ent")
+
+
+def load_inputs(path_1, path_2=None, id=None, embedder=None):
+    """-> inputs dict {"id", "receptor": {x, pos, seq[, structure, aa_coords, bb_coords]}, "ligand": {...}}.
 
     path_1 alone: a two-chain record (data/db5_test/<id>.pt layout).  path_1 + path_2: one single-chain record each
-    ({"x", "pos", "seq"}).  Raw PDB files need the ESM-2 front end, which is not part of this path.
+    ({"x", "pos", "seq"}), or two raw PDB files (src/inference_base.py:563-575) -- those need `embedder`, a callable
+    seq -> [len(seq), 1280] ESM-2 representation (pdbio.EsmEmbedder).
     """
-    for p in (path_1, path_2):
-        if p is not None and str(p).lower().endswith((".pdb", ".ent", ".cif")):
-            raise NotImplementedError(
-                "%s: raw structure files need the PDB parser + ESM-2 650M embedding front end of the reference "
-                "(src/inference_base.py:72-306; biotite and fair-esm are not available here).  Pass the reference's "
-                "pre-embedded record (.pt with x / pos / seq per chain) instead." % p)
+    is_pdb = [p is not None and str(p).lower().endswith(STRUCTURE_EXT) for p in (path_1, path_2)]
+    if any(is_pdb):
+        if not all(is_pdb):
+            raise ValueError("give either two PDB files or pre-embedded records, not a mix: %s, %s" % (path_1, path_2))
+        if embedder is None:
+            raise RuntimeError(
+                "%s: raw structure files need ESM-2 650M embeddings (src/inference_base.py:294-306).  Pass --esm_dir with a local "
+                "Hugging Face export of esm2_t33_650M_UR50D, or use the reference's pre-embedded records (.pt with x / pos / "
+                "seq per chain)." % path_1)
+        return pdbio.record_from_pdbs(path_1, path_2, embedder, id=id)
     if path_2 is None or path_2 == path_1:
         rec = load_db5_record(path_1)
     else:
@@ -102,31 +117,75 @@ def ligand_rmsd(lig_pos, native_lig_pos):
     return _rmsd(torch.as_tensor(lig_pos)[:, 1].double().cpu(), torch.as_tensor(native_lig_pos)[:, 1].double().cpu())
 
 
+def _rank():
+    return torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+
+
+def write_samples(out_dir, inputs, batch, poses, centre_mode, device):
+    """One structure file per sample (src/inference.py:401-412): all-atom when the inputs came from PDB files."""
+    if "structure" in inputs["ligand"]:
+        rot = torch.stack([p[1] for p in poses]).to(device)
+        tr = torch.stack([p[2] for p in poses]).to(device)
+        aa = pdbio.modify_aa_coords(inputs["ligand"]["aa_coords"], inputs["ligand"]["bb_coords"], rot, tr,
+                                    centre_mode=centre_mode, device=device).cpu()
+        for i in range(len(poses)):
+            pdbio.write_complex_pdb(os.path.join(out_dir, "%s_%d.pdb" % (inputs["id"], i)), inputs["receptor"], inputs["ligand"], aa[i])
+    else:
+        for i, p in enumerate(poses):
+            write_backbone_pdb(os.path.join(out_dir, "%s_%d.pdb" % (inputs["id"], i)), batch["rec_pos"], p[0],
+                               inputs["receptor"]["seq"], inputs["ligand"]["seq"])
+
+
 def run(args, model, inputs, batch, device):
     """Per-sample metric rows + one structure file per sample (src/inference.py:375-413)."""
     centre_mode = int(getattr(args, "centre_mode", 1))
+    ode = bool(getattr(args, "ode", False))
+    trj_dir = getattr(args, "out_trj_dir", None)
     rows = []
-    native_lig = batch["lig_pos"].clone()
+    if getattr(args, "native_dir", None):
+        nat = pdbio.get_native(os.path.join(args.native_dir, "%s.pdb" % inputs["id"]))     # src/inference_base.py:478-479
+        native_rec, native_lig = nat[0], nat[1]
+    else:
+        native_rec, native_lig = batch["rec_pos"], batch["lig_pos"].clone()
+    if getattr(args, "get_gt_energy", False):
+        # Sampler.run_sampling, get_gt_energy branch (src/inference_mlsb.py:190-199): score the input pose, no sampling
+        energy, clashes = model.gt_energy(batch)
+        met = compute_metrics_batch(batch["rec_pos"], batch["lig_pos"][None], native_rec, native_lig, device=device).cpu()
+        row = {"id": inputs["id"]}
+        row.update({k: float(met[0, j]) for j, k in enumerate(METRIC_KEYS)})
+        row.update({"energy": energy, "num_clashes": clashes})
+        return [row]
+    frames = None
     if getattr(args, "reference_rng", False):
-        poses = []
+        poses, frames = [], []
         for i in range(args.num_samples):
+            trj = [] if trj_dir else None
             rec_pos, lig_pos, rot_update, tr_update, output = Euler_Maruyama_sampler(
                 model=model, batch=dict(batch), num_steps=args.num_steps, device=device,
                 use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing,
-                tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode)
+                tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode, ode=ode,
+                trajectory=trj)
             poses.append((lig_pos.cpu(), rot_update.view(3).cpu(), tr_update.view(3).cpu(), float(output["energy"]),
                           int(output["num_clashes"])))
+            frames.append(trj)
+    elif trj_dir:
+        model.set_complex(batch)
+        res = model.sample(batch["lig_pos"], args.num_samples, num_steps=args.num_steps, tr_noise_scale=args.tr_noise_scale,
+                           rot_noise_scale=args.rot_noise_scale, use_clash_force=args.use_clash_force,
+                           noise_annealing=args.noise_annealing, centre_mode=centre_mode, seed=args.seed, ode=ode, record=True)
+        poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
+                  int(res["num_clashes"][i])) for i in range(args.num_samples)]
+        frames = [list(res["frames"][:, i].cpu()) for i in range(args.num_samples)]
     else:
         res = sample_trajectories(model, batch, args.num_samples, num_steps=args.num_steps,
                                   use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing,
                                   tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale,
-                                  centre_mode=centre_mode, seed=args.seed, gather_poses=True)
+                                  centre_mode=centre_mode, seed=args.seed, gather_poses=True, ode=ode)
         poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
                   int(res["num_clashes"][i])) for i in range(args.num_samples)]
-    rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
     # metrics of every pose in one launch (src/inference.py:393 calls compute_metrics per sample); the native pose is the
-    # one in the input record, like the reference's `native = inputs[...]['bb_coords']`
-    met = compute_metrics_batch(batch["rec_pos"], torch.stack([p[0] for p in poses]), batch["rec_pos"], native_lig,
+    # one in the input record unless --native_dir is given, like the reference's `native = inputs[...]['bb_coords']`
+    met = compute_metrics_batch(batch["rec_pos"], torch.stack([p[0] for p in poses]), native_rec, native_lig,
                                 device=device).cpu()
     for i, (lig_pos, rot_u, tr_u, energy, clashes) in enumerate(poses):
         row = {"id": inputs["id"], "index": str(i)}
@@ -134,14 +193,29 @@ def run(args, model, inputs, batch, device):
         row.update({"energy": energy, "num_clashes": clashes, "rot_update": " ".join("%.6f" % float(v) for v in rot_u),
                     "tr_update": " ".join("%.6f" % float(v) for v in tr_u)})
         rows.append(row)
-        if rank == 0 and getattr(args, "out_dir", None):
-            write_backbone_pdb(os.path.join(args.out_dir, "%s_%d.pdb" % (inputs["id"], i)), batch["rec_pos"], lig_pos,
-                               inputs["receptor"]["seq"], inputs["ligand"]["seq"])
+    if _rank() == 0:
+        if getattr(args, "out_dir", None):
+            write_samples(args.out_dir, inputs, batch, poses, centre_mode, device)
+        if trj_dir and frames:
+            os.makedirs(trj_dir, exist_ok=True)
+            for i, trj in enumerate(frames):
+                pdbio.write_trajectory_pdb(os.path.join(trj_dir, "%s_p%d.pdb" % (inputs["id"], i)), batch["rec_pos"], trj,
+                                           inputs["receptor"]["seq"], inputs["ligand"]["seq"])
     return rows
 
 
-def main(args):
-    """src/inference.py:418-495"""
+def init_distributed():
+    """One process per GPU under torchrun: NCCL group + device from LOCAL_RANK.  No-op for a plain `python` launch."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and torch.distributed.is_available() and not torch.distributed.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world
+
+
+def main(args, embedder=None):
+    """src/inference.py:418-495.  `embedder` overrides the ESM-2 front end (seq -> [n,1280]); default: --esm_dir."""
     paths_list = []
     if args.paths:
         id, p1, p2 = args.paths
@@ -153,23 +227,27 @@ def main(args):
         if os.path.exists(args.csv):
             with open(args.csv, "r") as f:
                 for row in csv.reader(f):
-                    paths_list.append((row[0], row[1], row[2] if len(row) > 2 else row[1]))
+                    if row:
+                        paths_list.append((row[0], row[1], row[2] if len(row) > 2 else row[1]))
         else:
             print("CSV file does not exist.")
     os.makedirs(args.out_dir, exist_ok=True)
-    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
-    if device is None:
+    if not torch.cuda.is_available():
         raise RuntimeError("dfmdock_b200.inference needs a CUDA (sm_100a) device; there is no CPU path")
+    init_distributed()
+    device = torch.device("cuda", torch.cuda.current_device())
     model = Score_Model.load_from_checkpoint(args.ckpt, map_location=device)
     model.to(device).eval()
+    if embedder is None and getattr(args, "esm_dir", None):
+        embedder = pdbio.EsmEmbedder(args.esm_dir, device=device)
     results = []
     for id, p1, p2 in paths_list:
-        inputs = load_inputs(p1, p2, id=id)
+        inputs = load_inputs(p1, p2, id=id, embedder=embedder)
         batch = batch_from_record(inputs, pos_width=model.pos_width)
         results.extend(run(args, model, inputs, batch, device))
     os.makedirs(args.out_csv_dir, exist_ok=True)
     out = os.path.join(args.out_csv_dir, args.out_csv)
-    if results:
+    if results and _rank() == 0:
         with open(out, "w", newline="") as f:
             w = csv.DictWriter(f, fieldnames=list(results[0].keys()))
             w.writeheader()
@@ -178,7 +256,8 @@ def main(args):
     return results
 
 
-def inference(in_1, in_2=None, ckpt=None, variant="pinder", num_samples=None, num_steps=40, out="output.pdb", seed=None):
+def inference(in_1, in_2=None, ckpt=None, variant="pinder", num_samples=None, num_steps=40, out="output.pdb", seed=None,
+              embedder=None, esm_dir=None):
     """Dock one complex and write the lowest-energy pose (src/inference.py:500-567; variant="base":
     src/inference_base.py:601-670).  Returns {"energy", "rot_update", "tr_update", "lig_pos", "index"}."""
     if variant == "pinder":
@@ -194,13 +273,20 @@ def inference(in_1, in_2=None, ckpt=None, variant="pinder", num_samples=None, nu
     device = torch.device("cuda", torch.cuda.current_device())
     model = Score_Model.load_from_checkpoint(ckpt, map_location=device)
     model.to(device).eval()
-    inputs = load_inputs(in_1, in_2)
+    if embedder is None and esm_dir:
+        embedder = pdbio.EsmEmbedder(esm_dir, device=device)
+    inputs = load_inputs(in_1, in_2, embedder=embedder)
     batch = batch_from_record(inputs, pos_width=model.pos_width)
     res = sample_trajectories(model, batch, num_samples, num_steps=num_steps, use_clash_force=use_clash_force,
                               centre_mode=centre_mode, seed=0 if seed is None else seed, gather_poses=True)
     best = res["best"]
     lig = res["lig_pos"][best].cpu()
-    if out:
+    if out and "structure" in inputs["ligand"]:
+        # src/inference.py:558-567 / src/inference_base.py:661-670: best pose, all-atom
+        aa = pdbio.modify_aa_coords(inputs["ligand"]["aa_coords"], inputs["ligand"]["bb_coords"], res["rot_update"][best][None],
+                                    res["tr_update"][best][None], centre_mode=centre_mode, device=device)[0]
+        pdbio.write_complex_pdb(out, inputs["receptor"], inputs["ligand"], aa)
+    elif out:
         write_backbone_pdb(out, batch["rec_pos"], lig, inputs["receptor"]["seq"], inputs["ligand"]["seq"])
     return {"energy": float(res["energy"][best]), "rot_update": res["rot_update"][best].cpu(),
             "tr_update": res["tr_update"][best].cpu(), "lig_pos": lig, "index": best}
@@ -227,6 +313,12 @@ def build_parser():
                         help="serial trajectories with the reference's RNG consumption order instead of batched Philox")
     parser.add_argument("--centre_mode", type=int, default=1, choices=[0, 1],
                         help="1: rotate about the N/CA/C centroid (src/inference.py), 0: CA centroid (src/inference_base.py)")
+    parser.add_argument("--native_dir", type=str, default=None, help="<native_dir>/<id>.pdb = native complex (src/inference_base.py:478)")
+    parser.add_argument("--esm_dir", type=str, default=None,
+                        help="local Hugging Face export of esm2_t33_650M_UR50D; required for raw PDB inputs")
+    parser.add_argument("--ode", action="store_true", help="probability-flow ODE instead of the reverse SDE (inference_mlsb.py)")
+    parser.add_argument("--out_trj_dir", type=str, default=None, help="write every sample's trajectory as a multi-MODEL PDB")
+    parser.add_argument("--get_gt_energy", action="store_true", help="score the input pose at t=1e-5 instead of sampling")
     return parser
 
 

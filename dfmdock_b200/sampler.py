@@ -14,7 +14,10 @@ from . import distributed as dist_utils
 
 
 def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=1, eps=1e-3, use_clash_force=False,
-                           noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0):
+                           noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, ode=False,
+                           trajectory=None):
+    """ode / trajectory are the two extras of the class-form sampler (src/inference_mlsb.py:264-350): the
+    probability-flow branch of torch_reverse, and a list that receives lig_pos after the random init and every step."""
     from scipy.spatial.transform import Rotation
 
     dev = model.device
@@ -32,6 +35,8 @@ def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=
     tr0 = torch.normal(0.0, 30.0, size=(1, 3), device=dev)
     lig_pos, tr_update, rot_update = model.randomize_pose(lig_pos0, 1, rot0=rot0[None], tr0=tr0, centre_mode=centre_mode)
 
+    if trajectory is not None:
+        trajectory.append(lig_pos[0].clone())
     output = None
     with torch.no_grad():
         for i in range(num_steps):
@@ -49,7 +54,9 @@ def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=
                 ns_tr, ns_rot = tr_noise_scale, rot_noise_scale
             z = torch.cat([torch.randn(1, 3, device=dev), torch.randn(1, 3, device=dev)], dim=0)   # rot, then tr
             model.reverse_step(lig_pos, rot_update, tr_update, output["tr_score"], output["rot_score"], t_host, dt_host,
-                               ns_rot, ns_tr, z=z[None], use_clash_force=use_clash_force, centre_mode=centre_mode)
+                               ns_rot, ns_tr, z=z[None], use_clash_force=use_clash_force, centre_mode=centre_mode, ode=ode)
+            if trajectory is not None:
+                trajectory.append(lig_pos[0].clone())
             if is_last:
                 batch["rec_pos"] = rec_pos
                 batch["lig_pos"] = lig_pos[0]
@@ -59,7 +66,7 @@ def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=
 
 def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_clash_force=False, noise_annealing=False,
                         tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, seed=0, max_batch=None, group=None,
-                        gather_poses=False):
+                        gather_poses=False, ode=False):
     """All `num_samples` trajectories of one complex.  Under torch.distributed each rank runs a contiguous slice
     (trajectory k always uses Philox subsequence k, so the result does not depend on the number of ranks) and the
     [T,8] result table (rot_update 3, tr_update 3, energy, num_clashes) is all-gathered once.
@@ -78,7 +85,8 @@ def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_c
         c1 = min(hi, c0 + step)
         chunks.append(model.sample(batch["lig_pos"], c1 - c0, num_steps=num_steps, eps=eps, tr_noise_scale=tr_noise_scale,
                                    rot_noise_scale=rot_noise_scale, use_clash_force=use_clash_force,
-                                   noise_annealing=noise_annealing, centre_mode=centre_mode, seed=seed, stream_base=c0))
+                                   noise_annealing=noise_annealing, centre_mode=centre_mode, seed=seed, stream_base=c0,
+                                   ode=ode))
     if chunks:
         local = {k: torch.cat([c[k] for c in chunks], dim=0) for k in chunks[0]}
     else:

@@ -249,12 +249,19 @@ class Score_Model:
                 "dfm_reverse_step")
 
     def sample(self, lig_pos0, num_traj, num_steps=40, eps=1e-3, tr_noise_scale=0.5, rot_noise_scale=0.5,
-               use_clash_force=False, noise_annealing=False, centre_mode=0, seed=0, stream_base=0, precision=None):
+               use_clash_force=False, noise_annealing=False, centre_mode=0, seed=0, stream_base=0, precision=None,
+               ode=False, record=False):
         """num_traj independent reverse-diffusion trajectories of the current complex, in lock step, on this GPU.
 
         Equivalent of the reference's serial driver loop around Euler_Maruyama_sampler (inference_base.py:644-657);
-        trajectory k draws from Philox subsequence (seed, stream_base + k).
+        trajectory k draws from Philox subsequence (seed, stream_base + k).  ode=True takes the probability-flow branch of
+        torch_reverse (so3_diffuser.py:366-367; Sampler.Euler_Maruyama_sampler(ode=...), inference_mlsb.py:264-350).
+        record=True additionally returns "frames" [num_steps + 1, B, L, 3, 3]: the initial pose and the pose after every
+        step (rec_trj / lig_trj of inference_mlsb.py:273-348); it runs the same kernels step by step from the host.
         """
+        if record:
+            return self._sample_recorded(lig_pos0, num_traj, num_steps, eps, tr_noise_scale, rot_noise_scale, use_clash_force,
+                                         noise_annealing, centre_mode, seed, stream_base, precision, ode)
         self._need_ctx()
         R, L = self._complex
         dev = self.device
@@ -267,13 +274,54 @@ class Score_Model:
         }
         ws, nws = self._workspace(B)
         flags = self._flags(False, precision, use_clash_force=use_clash_force, noise_annealing=noise_annealing,
-                            centre_mode=centre_mode)
+                            centre_mode=centre_mode, ode=ode)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().dfm_sample(
                 self._ctx, B, _lib.ptr(lig0), int(num_steps), float(eps), float(tr_noise_scale), float(rot_noise_scale),
                 flags, seed, stream_base, _lib.ptr(out["lig_pos"]), _lib.ptr(out["rot_update"]), _lib.ptr(out["tr_update"]),
                 _lib.ptr(out["energy"]), _lib.ptr(out["num_clashes"]), ws, nws, self._stream()), "dfm_sample")
         return out
+
+    def _sample_recorded(self, lig_pos0, num_traj, num_steps, eps, tr_noise_scale, rot_noise_scale, use_clash_force,
+                         noise_annealing, centre_mode, seed, stream_base, precision, ode):
+        """dfm_sample unrolled on the host (same kernels, same Philox keys -> same poses) with every frame kept."""
+        if num_steps < 2:
+            raise ValueError("num_steps must be >= 2")
+        B = int(num_traj)
+        lig, tr_u, rot_u = self.randomize_pose(lig_pos0, B, seed=seed, stream_base=stream_base, centre_mode=centre_mode)
+        frames = [lig.clone()]
+        ts = torch.linspace(1.0, eps, num_steps)            # fp32, like the reference (inference_base.py:404)
+        dt = float(ts[0] - ts[1])
+        t_dev = torch.empty(B, device=self.device)
+        o = None
+        for i in range(num_steps):
+            t = float(ts[i])
+            last = i == num_steps - 1
+            t_dev.fill_(t)
+            o = self.score(lig, t_dev, seed=seed, stream_base=stream_base, forward_index=i, precision=precision)
+            if noise_annealing:
+                ns_tr = ns_rot = t
+            elif last:
+                ns_tr = ns_rot = 0.0
+            else:
+                ns_tr, ns_rot = tr_noise_scale, rot_noise_scale
+            self.reverse_step(lig, rot_u, tr_u, o["tr_score"], o["rot_score"], t, dt, ns_rot, ns_tr, seed=seed,
+                              stream_base=stream_base, step_index=i, use_clash_force=use_clash_force,
+                              centre_mode=centre_mode, ode=ode)
+            frames.append(lig.clone())
+            if last:
+                o = self.score(lig, t_dev, seed=seed, stream_base=stream_base, forward_index=num_steps, precision=precision,
+                               want_energy=True)
+        return {"lig_pos": lig, "rot_update": rot_u, "tr_update": tr_u, "energy": o["energy"], "num_clashes": o["num_clashes"],
+                "frames": torch.stack(frames, dim=0)}
+
+    def gt_energy(self, batch):
+        """Energy / clash count of the pose in `batch` itself at t = 1e-5 (Sampler.run_sampling with get_gt_energy,
+        src/inference_mlsb.py:190-199) -> (energy float, num_clashes int)."""
+        b = dict(batch)
+        b["t"] = torch.zeros(1) + 1e-5
+        o = self.forward(b)
+        return float(o["energy"]), int(o["num_clashes"])
 
     def profile_enable(self, max_launches):
         _lib.check(_lib.load().dfm_profile_enable(self._ctx, int(max_launches)), "dfm_profile_enable")

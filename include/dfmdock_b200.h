@@ -167,6 +167,16 @@ int dfm_compute_metrics(int device, int T, int R, int L, const float* model_rec,
                         const float* model_lig, const float* native_rec, const float* native_lig, float* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- all-atom output ---------------------------------------------------------------------
+ * Replaces: modify_aa_coords -- the rigid transform the sampler accumulated (rot_update, tr_update) applied to the
+ * ligand's all-atom coordinates before the structure is written:
+ *   centre_mode 0: rotate about the ligand's backbone CA centroid   (src/inference_base.py:354-364; lig_bb [L,3,3])
+ *   centre_mode 1: rotate about the all-atom centroid of `atoms`    (src/inference.py:256-266; lig_bb may be NULL)
+ *   atoms [A,3] (shared by all poses), rot_update [T,3] axis-angle, tr_update [T,3]  ->  out [T,A,3]; DEVICE pointers.
+ * Needs no context; stream-ordered on `stream`; returns 0 or a negative DFM_E* code. */
+int dfm_transform_atoms(int device, int T, int A, int L, int centre_mode, const float* atoms, const float* lig_bb,
+                        const float* rot_update, const float* tr_update, float* out, void* stream);
+
 const char* dfm_last_error(void);
 const char* dfm_version(void);
 void dfm_destroy(dfm_ctx* ctx);

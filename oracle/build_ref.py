@@ -72,5 +72,27 @@ def main(quiet=False, force=False):
         print("wrote", OUT, [(g["ckpt"], g["complex"], g["t"], float(g["energy"])) for g in golden])
 
 
+def extract_all_db5(quiet=False):
+    """BASELINE config #5 inputs: every complex of data/db5_test/test.txt -> oracle/_ref/db5_all/<id>.pt (65 MB, git-ignored;
+    only needed for profiles/run_db5_set.py -- remove the directory afterwards to keep gpurun snapshots small)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        print("reference tree not mounted; nothing to do")
+        return
+    from dfmdock_b200.checkpoint import load_db5_record
+    root = os.path.join(ref_shims.REFERENCE_ROOT, "data", "db5_test")
+    out = os.path.join(OUT, "db5_all")
+    os.makedirs(out, exist_ok=True)
+    ids = open(os.path.join(root, "test.txt")).read().split()
+    for cid in ids:
+        rec = load_db5_record(os.path.join(root, cid + ".pt"))
+        torch.save(rec, os.path.join(out, cid + ".pt"))
+        if not quiet:
+            print(cid, rec["receptor"]["pos"].shape[0], rec["ligand"]["pos"].shape[0])
+
+
 if __name__ == "__main__":
-    main(force="--force" in sys.argv)
+    if "--all-db5" in sys.argv:
+        extract_all_db5()
+    else:
+        main(force="--force" in sys.argv)

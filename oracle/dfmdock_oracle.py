@@ -335,8 +335,11 @@ def r3_g(t, lo=0.1, hi=30.0):
     return lo * (hi / lo) ** t * np.sqrt(2 * (np.log(hi) - np.log(lo)))
 
 
-def reverse_increment(g_t, score, dt, z_scaled):
-    """torch_reverse, SDE branch (so3_diffuser.py:363-365 = r3_diffuser.py:50-52); dt a 0-d fp32 tensor."""
+def reverse_increment(g_t, score, dt, z_scaled, ode=False):
+    """torch_reverse (so3_diffuser.py:363-368 = r3_diffuser.py:50-55); dt a 0-d fp32 tensor.  ode=True is the
+    probability-flow branch: half the drift, no noise."""
+    if ode:
+        return (0.5 * (g_t ** 2) * score * dt).float()
     return ((g_t ** 2) * score * dt + g_t * torch.sqrt(dt) * z_scaled).float()
 
 
@@ -458,7 +461,7 @@ def clash_force_autograd(rec_pos, lig_pos):
 
 def euler_maruyama_sampler(net: OracleNet, batch, num_steps=40, eps=1e-3, use_clash_force=False,
                            noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5,
-                           centre_mode=0, noise: Optional[dict] = None, record: Optional[list] = None):
+                           centre_mode=0, noise: Optional[dict] = None, record: Optional[list] = None, ode=False):
     """Restatement of Euler_Maruyama_sampler.
 
     noise (all optional): {"rot0": [3,3], "tr0": [1,3], "edges": [S+1,N,K] or "exp": [S+1,N,N-20],
@@ -503,9 +506,9 @@ def euler_maruyama_sampler(net: OracleNet, batch, num_steps=40, eps=1e-3, use_cl
         else:
             ns_tr, ns_rot = tr_noise_scale, rot_noise_scale
         z_rot = noise["z_rot"][i] if "z_rot" in noise else torch.randn(1, 3)
-        rot = reverse_increment(so3_g(float(t)), out["rot_score"], dt, ns_rot * z_rot)
+        rot = reverse_increment(so3_g(float(t)), out["rot_score"], dt, ns_rot * z_rot, ode)
         z_tr = noise["z_tr"][i] if "z_tr" in noise else torch.randn(1, 3)
-        tr = reverse_increment(r3_g(float(t)), out["tr_score"], dt, ns_tr * z_tr)
+        tr = reverse_increment(r3_g(float(t)), out["tr_score"], dt, ns_tr * z_tr, ode)
         lig_pos = modify_coords(lig_pos, rot, tr, centre_mode)
         tr_update = tr_update + tr
         rot_update = rot_compose(rot_update, rot)
@@ -519,3 +522,15 @@ def euler_maruyama_sampler(net: OracleNet, batch, num_steps=40, eps=1e-3, use_cl
         if last:
             out = fwd(num_steps, torch.ones(1) * t)
     return rec_pos, lig_pos, rot_update, tr_update, out
+
+
+# ----------------------------------------------------------------------------------------------
+# all-atom output
+
+def modify_aa_coords(x, bb_coords, rot_aa, tr, centre_mode=0):
+    """modify_aa_coords: centre_mode 0 = src/inference_base.py:354-364 (CA centroid of the backbone),
+    1 = src/inference.py:256-266 (centroid of the all-atom coordinates).  numpy float64 like the reference."""
+    x = np.asarray(x)
+    center = np.asarray(bb_coords, dtype=np.float64)[:, 1].mean(axis=0) if centre_mode == 0 else x.mean(axis=0)
+    rot = aa_to_mat(torch.as_tensor(rot_aa).float().view(1, 3)).squeeze().cpu().numpy()
+    return (x - center) @ rot.T + center + torch.as_tensor(tr).float().view(1, 3).cpu().numpy()

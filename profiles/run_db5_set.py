@@ -1,0 +1,84 @@
+"""BASELINE config #5: the full data/db5_test set (25 complexes, N = 197 .. 2548), 40 trajectories x 40 steps each with
+weights/pinder_0.ckpt + clash force, through the public API (sample_trajectories + compute_metrics_batch).
+
+    python profiles/run_db5_set.py                                   # 1 GPU
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 profiles/run_db5_set.py   # trajectory-sharded
+
+Inputs: oracle/_ref/pinder_0.pt and oracle/_ref/db5_all/<id>.pt (python oracle/build_ref.py --all-db5 in the build
+container; falls back to the three complexes of oracle/_ref/).  Prints one line per complex and the set totals; writes
+gpurun_out/db5_c5.csv with the reference's CSV columns for the lowest-energy sample of each complex.
+"""
+import csv
+import glob
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from dfmdock_b200 import Score_Model  # noqa: E402
+from dfmdock_b200.features import batch_from_record  # noqa: E402
+from dfmdock_b200.inference import init_distributed  # noqa: E402
+from dfmdock_b200.metrics import KEYS, compute_metrics_batch  # noqa: E402
+from dfmdock_b200.sampler import sample_trajectories  # noqa: E402
+
+T, S = int(os.environ.get("C5_SAMPLES", "40")), int(os.environ.get("C5_STEPS", "40"))
+
+
+def main():
+    world = init_distributed()
+    rank = torch.distributed.get_rank() if world > 1 else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    ck = torch.load(os.path.join(ref, "pinder_0.pt"), weights_only=False)
+    model = Score_Model(ck["state_dict"], ck["hparams"], precision="fp16").to(dev)
+    paths = sorted(glob.glob(os.path.join(ref, "db5_all", "*.pt"))) or sorted(glob.glob(os.path.join(ref, "db5_*.pt")))
+    rows, total_ms, total_ps = [], 0.0, 0
+    # warm-up (allocator, module load) on the first complex
+    b0 = batch_from_record(torch.load(paths[0], weights_only=False), pos_width=model.pos_width)
+    sample_trajectories(model, b0, max(world, 2), num_steps=3, use_clash_force=True, centre_mode=1, seed=1)
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for p in paths:
+        cid = os.path.splitext(os.path.basename(p))[0].replace("db5_", "")
+        batch = batch_from_record(torch.load(p, weights_only=False), pos_width=model.pos_width)
+        R, L = batch["rec_pos"].shape[0], batch["lig_pos"].shape[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        res = sample_trajectories(model, batch, T, num_steps=S, use_clash_force=True, centre_mode=1, seed=42, gather_poses=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        ms = float(ms)
+        met = compute_metrics_batch(batch["rec_pos"], res["lig_pos"], batch["rec_pos"], batch["lig_pos"], device=dev).cpu()
+        best = res["best"]
+        total_ms += ms
+        total_ps += T * S
+        row = {"id": cid, "index": str(best), "n_rec": R, "n_lig": L}
+        row.update({k: float(met[best, j]) for j, k in enumerate(KEYS)})
+        row.update({"energy": float(res["energy"][best]), "num_clashes": int(res["num_clashes"][best]), "ms": ms,
+                    "best_dockq_of_40": float(torch.nan_to_num(met[:, 4], nan=0.0).max())})
+        rows.append(row)
+        if rank == 0:
+            print("%-5s R=%4d L=%4d  %8.1f ms  %7.0f pose-steps/s  lowest energy %8.2f (sample %2d: DockQ %.3f, L-RMSD %6.2f)  best DockQ of %d: %.3f"
+                  % (cid, R, L, ms, T * S / (ms * 1e-3), row["energy"], best, row["DockQ"], row["l_rmsd"], T, row["best_dockq_of_40"]), flush=True)
+    wall = time.perf_counter() - wall0
+    if rank == 0:
+        print("c5 total: %d complexes x %d traj x %d steps on %d GPU(s): sampling %.2f s (device time, max over ranks), wall %.2f s incl. "
+              "H2D of the records and metrics; %.0f pose-steps/s" % (len(rows), T, S, world, total_ms * 1e-3, wall, total_ps / (total_ms * 1e-3)))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "db5_c5_%dgpu.csv" % world), "w", newline="") as f:
+            w = csv.DictWriter(f, fieldnames=list(rows[0].keys()))
+            w.writeheader()
+            w.writerows(rows)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -149,7 +149,7 @@ def test_bench_roofline_arithmetic():
 
 
 def test_inference_cli_surface_matches_reference_flags(tmp_path):
-    """src/inference.py:569-589: same flag names / defaults; raw PDB inputs are refused loudly (ESM front end is out of scope)."""
+    """src/inference.py:569-589: same flag names / defaults; raw PDB inputs without ESM-2 weights are refused loudly."""
     from dfmdock_b200 import inference as inf
     p = inf.build_parser()
     a = p.parse_args(["--paths", "x", "a.pt", "b.pt"])
@@ -158,8 +158,11 @@ def test_inference_cli_surface_matches_reference_flags(tmp_path):
     assert not a.use_clash_force and not a.noise_annealing
     with pytest.raises(SystemExit):
         p.parse_args([])                       # --paths | --csv is required, like the reference
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="esm_dir"):
         inf.load_inputs("1A2K_r_b.pdb", "1A2K_l_b.pdb")
+    with pytest.raises(ValueError):
+        inf.load_inputs("1A2K_r_b.pdb", "1A2K_l_b.pt")
+    assert (a.ode, a.out_trj_dir, a.native_dir, a.esm_dir, a.get_gt_energy) == (False, None, None, None, False)
     # record loading + backbone writer
     from dfmdock_b200.features import synthetic_complex
     b = synthetic_complex(6, 5, seed=1)
