@@ -16,6 +16,9 @@
 // SiLU(x) = h + h * tanh(h) with h = x/2: one MUFU and one HFMA2 per element pair.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -54,6 +57,18 @@ constexpr int MMA_REGS = 40;
 #endif
 #ifndef EWS_TIMING
 #define EWS_TIMING 0   // 1: accumulate cycles spent in barrier waits per role into Params::timing (diagnostic builds)
+#endif
+#ifndef EWS_ROW_INTERLEAVE
+#define EWS_ROW_INTERLEAVE 0   // (measured slower: 1.29 vs 1.21 ms) producer warp w builds slots {w&7, (w&7)+8, ...} of its residue instead of 8 consecutive slots:
+#endif                         // every warp gets the same mix of kNN slots (two table gathers) and far slots (one)
+#ifndef EWS_EPI_V3
+#define EWS_EPI_V3 1      // epilogue on tcgen05.ld.16x256b fragments: a thread holds 4 rows x 16 column pairs, so the gated
+#endif                    // segment sum is mostly in-thread FMAs (14 shuffle steps instead of 63)
+#ifndef EWS_EPI_PIPE
+#define EWS_EPI_PIPE 1    // epilogue: 8-column tcgen05.ld double buffered (next chunk in flight while this one is computed)
+#endif
+#ifndef EWS_EPI_CONST
+#define EWS_EPI_CONST 0   // epilogue: b2/2 and wa from the parameter block's constant bank instead of LDS (measured slower: LDC.64 pairs)
 #endif
 #ifndef EWS_USE_ALO
 #define EWS_USE_ALO 0     // carry A_i as fp16 hi + lo (1) or a single fp16 (0)
@@ -126,6 +141,26 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// 16 lanes x 256 bit x 2: lane t gets, for the two 8-column blocks b = 0, 1 at [taddr]:
+//   r[4b + 0..1] = (row t/4,     columns 8b + 2(t%4) + {0,1}),  r[4b + 2..3] = (row t/4 + 8, same columns)
+// (layout measured with profiles/probes/tmem_ld_shapes.cu)
+__device__ __forceinline__ void tmem_ld16x256_x2_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// wait for all outstanding tcgen05.ld; the registers of the chunk about to be consumed are tied to the wait so that no
+// use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
 
 // ---- shared-memory accessors on 32-bit shared-space addresses (LDS/STS instead of generic LD/ST) ----------
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -183,6 +218,8 @@ struct Params {
   const float* ba;          // [1]
   __half* agg16;            // [B*N, 256] fp16(agg x 2^-6) out
   __half* mstar;            // [B*L, 64, 256] fp16 (m* x 2^-6), last layer only
+  uint32_t b2h[128];        // b2/2 as packed half2 (constant-bank operands of the epilogue)
+  uint32_t wah[128];        // wa as packed half2
   unsigned long long* timing;   // EWS_TIMING: [8] cycles {prod wait bfull, prod total, loader wait empty, loader total,
                                 //                        mma wait full, mma wait acce, epi wait accf, epi total}
 };
@@ -195,6 +232,24 @@ template <int NR>
 __device__ __forceinline__ void lane_transpose_sum_h2(uint32_t* v, int lane) {
 #pragma unroll
   for (int o = 16, n = NR; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+    const int half = n >> 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const uint32_t send = up ? v[i] : v[i + half];
+      const uint32_t keep = up ? v[i + half] : v[i];
+      v[i] = h2add(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+}
+
+// NR packed registers summed over the lanes that differ in the bits OHI .. OLO (powers of two, OHI >= OLO), halving the
+// register count at every step: with NR = 16, OHI = 16, OLO = 4 lane l ends with v[0], v[1] = sums of registers
+// 2 (l >> 2) and 2 (l >> 2) + 1 over the 8 lanes that share l & 3
+template <int NR, int OHI, int OLO>
+__device__ __forceinline__ void lane_group_sum_h2(uint32_t* v, int lane) {
+#pragma unroll
+  for (int o = OHI, n = NR; o >= OLO; o >>= 1, n >>= 1) {
     const bool up = (lane & o) != 0;
     const int half = n >> 1;
 #pragma unroll
@@ -230,8 +285,19 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       vb2[tid] = __float2half_rn(0.5f * p.b2[tid]);
       vwa[tid] = __float2half_rn(p.wa[tid]);
       vwr[tid] = __float2half_rn(p.w1r[tid] * (0.5f / RAD_SCALE));
+#if EWS_EPI_V3
+      if (tid < 128) {
+        // fragment order of the 16x256b epilogue: [column half][t % 4][8-column block j] -> column pair ch*64 + 4 j + (t%4)
+        const int pr = (tid >> 6) * 64 + 4 * (tid & 15) + ((tid >> 4) & 3);
+        const __half2 b = __floats2half2_rn(0.5f * p.b2[2 * pr], 0.5f * p.b2[2 * pr + 1]);
+        const __half2 w = __floats2half2_rn(p.wa[2 * pr], p.wa[2 * pr + 1]);
+        reinterpret_cast<__half2*>(smem + OFF_VEC32)[tid] = b;
+        reinterpret_cast<__half2*>(smem + OFF_VEC32)[128 + tid] = w;
+      }
+#else
       reinterpret_cast<float*>(smem + OFF_VEC32)[tid] = 0.5f * p.b2[tid];
       reinterpret_cast<float*>(smem + OFF_VEC32)[256 + tid] = p.wa[tid];
+#endif
     }
   }
   if (tid == 0) {
@@ -256,12 +322,16 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 
   if (warp < NPROD) {
     // =================================== PRODUCERS ===================================================
-    // rows of this lane: r_i = warp*16 + 4 i + (lane >> 3), i = 0..3 (all in residue `warp >> 2` of the tile);
+    // rows of this lane: ring index idx = (lane >> 3) + 4 i, i = 0..1 -> tile row prow(idx), all in residue `warp >> 3`;
     // 16-byte chunk c8 = lane & 7 of each 128-byte K-block row.  Work item = (K block, pair of rows); the gathers of
     // item n+1 are in flight while item n is computed (two register buffers), across K blocks and across tiles.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
     const int c8 = lane & 7, rsub = lane >> 3;
-    const int r0 = warp * 8 + rsub;
+#if EWS_ROW_INTERLEAVE
+    auto prow = [&](int idx) -> int { return (warp >> 3) * 64 + (warp & 7) + 8 * idx; };
+#else
+    auto prow = [&](int idx) -> int { return warp * 8 + idx; };
+#endif
     const int4 pad_meta = make_int4(0, 40 * 66 + 32, -1, 0);
     // B_j is already in the S tile (loader warps, cp.async); this role gathers the two table rows of each edge into
     // registers one K block ahead (two buffers), forms u/2, applies SiLU and overwrites the 16-byte chunk in place.
@@ -272,7 +342,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     uint32_t soff[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int r = r0 + 4 * i;
+      const int r = prow(rsub + 4 * i);
       soff[i] = sbase + OFF_S + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
     }
     auto issue = [&](GBuf& g, uint32_t mslot, size_t aoff, int kb) {
@@ -304,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     };
     auto load_meta = [&](int tile) -> int4 {     // lanes 0..7: edge metadata of row warp*8 + lane of `tile`
       int4 mt = pad_meta;
-      const int r = warp * 8 + (lane & 7);
+      const int r = prow(lane & 7);
       const int node = tile * 2 + (r >> 6);
       if (tile < t_end && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
       return mt;
@@ -462,6 +532,124 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     unsigned long long tw0 = 0;
     const long long tstart = clock64();
     int it = 0;
+#if EWS_EPI_V3
+    // Fragment layout: lane t = (rg = t >> 2, cq = t & 3) holds rows rr(k) = q*32 + rg + 8 k (k = 0..3) and, for every
+    // 8-column block j = 0..15 of this warp's column half, the column pair 8 j + 2 cq + {0, 1}: m[k * 16 + j].
+    const int rg = lane >> 2, cq = lane & 3;
+    const uint32_t vx_s = sbase + OFF_VEC32 + (uint32_t)((ch * 4 + cq) * 16) * 4u;
+    const uint32_t part_row_s = sbase + OFF_PART + (uint32_t)(q * 32 + rg) * 4u;      // + 32 k bytes for row k
+    (void)erow; (void)vec_s; (void)vec32_s; (void)part_s;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int buf = it & 1;
+      const int node = tile * 2 + hn;
+      TWAIT(tw0, mbar_wait<200>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
+      uint32_t m[64];
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        uint32_t accA[8], accB[8];
+        uint32_t dA = 0, dB = 0;
+        uint4 bb = make_uint4(0, 0, 0, 0), ww = make_uint4(0, 0, 0, 0);
+        tmem_ld16x256_x2_issue(tbase, accA);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {          // n = hh * 8 + jj: row half hh (rows k = 2 hh, 2 hh + 1), blocks 2 jj, 2 jj + 1
+          const int hh = n >> 3, jj = n & 7;
+          uint32_t* cur = (n & 1) ? accB : accA;
+          uint32_t* nxt = (n & 1) ? accA : accB;
+          tmem_ld_wait8(cur);
+          if (n + 1 < 16) tmem_ld16x256_x2_issue(tbase + ((uint32_t)(((n + 1) >> 3) * 16) << 16) + (uint32_t)(((n + 1) & 7) * 16), nxt);
+          if ((jj & 1) == 0) {
+            bb = lds128(vx_s + (uint32_t)(jj >> 1) * 16u);
+            ww = lds128(vx_s + 512u + (uint32_t)(jj >> 1) * 16u);
+          }
+          const uint32_t b0 = (jj & 1) ? bb.z : bb.x, b1 = (jj & 1) ? bb.w : bb.y;
+          const uint32_t w0 = (jj & 1) ? ww.z : ww.x, w1 = (jj & 1) ? ww.w : ww.y;
+          const uint32_t x00 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), b0));
+          const uint32_t x10 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), b0));
+          const uint32_t x01 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), b1));
+          const uint32_t x11 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), b1));
+          m[(2 * hh) * 16 + 2 * jj] = x00; m[(2 * hh) * 16 + 2 * jj + 1] = x01;
+          m[(2 * hh + 1) * 16 + 2 * jj] = x10; m[(2 * hh + 1) * 16 + 2 * jj + 1] = x11;
+          dA = h2fma(x00, w0, dA); dA = h2fma(x01, w1, dA);
+          dB = h2fma(x10, w0, dB); dB = h2fma(x11, w1, dB);
+          if ((jj & 3) == 3) {      // 8 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
+            const float2 fa = h2f2(dA), fb = h2f2(dB);
+            dot[2 * hh] += fa.x + fa.y; dot[2 * hh + 1] += fb.x + fb.y;
+            dA = dB = 0;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
+      // gate logit: sum over the 4 lanes of a row, then over the two column halves (shared memory)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], 1);
+        dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], 2);
+      }
+      if (cq == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stsf(part_row_s + (uint32_t)ch * 512u + (uint32_t)k * 32u, dot[k]);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the 2 column halves of this row quarter
+      uint32_t gk[4];
+      {
+        // lane (rg, cq) evaluates the gate of row k = cq; the 4 lanes of a row group then exchange them
+        const float mine = cq == 0 ? dot[0] : cq == 1 ? dot[1] : cq == 2 ? dot[2] : dot[3];
+        const float other = ldsf(part_row_s + (uint32_t)(ch ^ 1) * 512u + (uint32_t)cq * 32u);
+        const float tot = (ch == 0 ? mine + other : other + mine) + ba;
+        const int slot = (q * 32 + rg + 8 * cq) & 63;
+        const bool valid = node < p.total_nodes && slot < p.K;
+        const float g = valid ? MSTAR_SCALE * __fdividef(1.f, 1.f + __expf(-tot)) : 0.f;
+        const uint32_t g2 = f2h2(g, g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gk[k] = __shfl_sync(0xffffffffu, g2, (lane & ~3) | k);
+      }
+      uint32_t sacc[16];
+      if (p.last) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[k * 16 + j] = h2mul(m[k * 16 + j], gk[k]);
+        }
+        if (node < p.total_nodes) {
+          const int b = node / p.N, i = node - b * p.N;
+          if (i >= p.R) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int slot = (q * 32 + rg + 8 * k) & 63;
+              if (slot < p.K) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + 2 * cq);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j * 4] = m[k * 16 + j];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[j] = h2add(h2add(m[j], m[16 + j]), h2add(m[32 + j], m[48 + j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          sacc[j] = h2fma(m[48 + j], gk[3], h2fma(m[32 + j], gk[2], h2fma(m[16 + j], gk[1], h2mul(m[j], gk[0]))));
+      }
+      lane_group_sum_h2<16, 16, 4>(sacc, lane);  // lane (rg, cq): blocks 2 rg, 2 rg + 1, column pair cq, summed over the 32 rows
+      const uint32_t ag = sbase + OFF_AGG + (uint32_t)buf * 4096u;
+      {
+        const float2 s0 = h2f2(sacc[0]), s1 = h2f2(sacc[1]);
+        const uint32_t a0 = ag + (uint32_t)(q * 256 + ch * 128 + 16 * rg + 2 * cq) * 4u;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a0), "f"(s0.x), "f"(s0.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a0 + 32u), "f"(s1.x), "f"(s1.y) : "memory");
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(5 + hn) : "memory");     // the 4 warps that hold this residue's rows
+      if (node < p.total_nodes) {
+        const uint32_t a0 = ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u;
+        // agg stays x 2^-6 in fp16 (the W3a image carries the 2^6): operand of node_tc.cu MODE_Z
+        *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
+      }
+    }
+#else
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int buf = it & 1;
       const int node = tile * 2 + hn, k = erow & 63;
@@ -471,6 +659,42 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
       uint32_t m[64];
       float dot = 0.f;
+#if EWS_EPI_PIPE && !EWS_EPI_FP32
+      {
+        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        uint32_t accA[8], accB[8];
+        auto chunks = [&](auto chc) {
+          constexpr int CH = decltype(chc)::value;
+          tmem_ld8_issue(taddr, accA);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            uint32_t* cur = (c & 1) ? accB : accA;
+            uint32_t* nxt = (c & 1) ? accA : accB;
+            tmem_ld_wait8(cur);
+            if (c + 1 < 16) tmem_ld8_issue(taddr + (c + 1) * 8, nxt);
+#if EWS_EPI_CONST
+            const uint4 bb = make_uint4(p.b2h[CH * 64 + c * 4], p.b2h[CH * 64 + c * 4 + 1], p.b2h[CH * 64 + c * 4 + 2], p.b2h[CH * 64 + c * 4 + 3]);
+            const uint4 ww = make_uint4(p.wah[CH * 64 + c * 4], p.wah[CH * 64 + c * 4 + 1], p.wah[CH * 64 + c * 4 + 2], p.wah[CH * 64 + c * 4 + 3]);
+#else
+            const uint4 bb = lds128(vec_s + (uint32_t)(c * 8) * 2u);
+            const uint4 ww = lds128(vec_s + 512u + (uint32_t)(c * 8) * 2u);
+#endif
+            const uint32_t x0 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), bb.x));
+            const uint32_t x1 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), bb.y));
+            const uint32_t x2 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), bb.z));
+            const uint32_t x3 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), bb.w));
+            m[c * 4 + 0] = x0; m[c * 4 + 1] = x1; m[c * 4 + 2] = x2; m[c * 4 + 3] = x3;
+            d0 = h2fma(x0, ww.x, d0); d1 = h2fma(x1, ww.y, d1); d2 = h2fma(x2, ww.z, d2); d3 = h2fma(x3, ww.w, d3);
+            if ((c & 3) == 3) {   // 4 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
+              const float2 f0 = h2f2(h2add(d0, d1)), f1 = h2f2(h2add(d2, d3));
+              dot += (f0.x + f0.y) + (f1.x + f1.y);
+              d0 = d1 = d2 = d3 = 0;
+            }
+          }
+        };
+        if (ch == 0) chunks(std::integral_constant<int, 0>{}); else chunks(std::integral_constant<int, 1>{});
+      }
+#else
       uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -519,6 +743,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         }
         }
       }
+#endif
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
       stsf(part_s + (uint32_t)ch * 512u, dot);
@@ -550,6 +775,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
       }
     }
+#endif
     if (EWS_TIMING && e == 0 && lane == 0) { atomicAdd(p.timing + 6, tw0); atomicAdd(p.timing + 7, (unsigned long long)(clock64() - tstart)); }
   }
   tc_fence_before();
@@ -575,6 +801,8 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
   p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
   p.agg16 = agg16; p.mstar = a.mstar;
+  memcpy(p.b2h, w.b2h_host, sizeof(p.b2h));
+  memcpy(p.wah, w.wah_host, sizeof(p.wah));
 #if EWS_TIMING
   static unsigned long long* tbuf = nullptr;
   if (!tbuf) { CUDA_TRY(cudaMalloc(&tbuf, 64)); CUDA_TRY(cudaMemset(tbuf, 0, 64)); }

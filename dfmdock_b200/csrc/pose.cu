@@ -193,43 +193,65 @@ k_reverse_step(int L, int all_atoms, int ode, float* __restrict__ lig_pos, float
 
 // U = -5 sum_{d<4} (4-d)^1.5 / (0.75 d) over all backbone atom pairs; F = mean over ligand atoms of dU/dx.
 // Analytic gradient of the reference's autograd formulation.
+// Residue-pair pruning: the atoms of a residue lie within rho = max(|N-CA|, |C-CA|) of its CA, so a residue pair whose
+// CA-CA distance exceeds 4 + rho_l + rho_r has no atom pair inside the 4 A cut-off -- exact, not an approximation.
 __global__ void __launch_bounds__(256)
 k_clash_force(int R, int L, const float* __restrict__ rec_pos, float* __restrict__ lig_pos,
               float* __restrict__ tr_update) {
+  constexpr int TILE = 64;
   __shared__ float red[3][8];
-  __shared__ float rs[256 * 3];
+  __shared__ float rs[TILE * 10];       // per receptor residue: N, CA, C coordinates + rho
   const int b = blockIdx.x, tid = threadIdx.x;
   float* x = lig_pos + (size_t)b * L * 9;
-  const int na = R * 3, nl = L * 3;
   float fx = 0.f, fy = 0.f, fz = 0.f;
-  for (int a0 = 0; a0 < na; a0 += 256) {
+  for (int r0 = 0; r0 < R; r0 += TILE) {
+    const int cnt = min(TILE, R - r0);
     __syncthreads();
-    if (a0 + tid < na) {
-      rs[tid * 3] = rec_pos[(a0 + tid) * 3]; rs[tid * 3 + 1] = rec_pos[(a0 + tid) * 3 + 1]; rs[tid * 3 + 2] = rec_pos[(a0 + tid) * 3 + 2];
+    for (int i = tid; i < cnt * 9; i += 256) rs[(i / 9) * 10 + (i % 9)] = rec_pos[(size_t)r0 * 9 + i];
+    __syncthreads();
+    if (tid < cnt) {
+      const float* q = rs + tid * 10;
+      const float ax = q[0] - q[3], ay = q[1] - q[4], az = q[2] - q[5];
+      const float cx = q[6] - q[3], cy = q[7] - q[4], cz = q[8] - q[5];
+      rs[tid * 10 + 9] = sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz));
     }
     __syncthreads();
-    const int cnt = min(256, na - a0);
-    for (int l = tid; l < nl; l += 256) {
-      const float lx = x[l * 3], ly = x[l * 3 + 1], lz = x[l * 3 + 2];
+    for (int l = tid; l < L; l += 256) {
+      float p[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) p[k] = x[l * 9 + k];
+      const float ax = p[0] - p[3], ay = p[1] - p[4], az = p[2] - p[5];
+      const float cx = p[6] - p[3], cy = p[7] - p[4], cz = p[8] - p[5];
+      const float reach = 4.f + sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz)) + 1e-3f;
       for (int r = 0; r < cnt; ++r) {
-        const float dx = lx - rs[r * 3], dy = ly - rs[r * 3 + 1], dz = lz - rs[r * 3 + 2];
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 < 16.f) {
-          const float d = sqrtf(d2);
-          const float g = 4.f - d;
-          const float sg = sqrtf(g);
-          const float dphi = -(1.5f * sg * d + g * sg) / (0.75f * d * d);
-          const float coef = -5.f * dphi / d;
-          fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
+        const float* q = rs + r * 10;
+        const float ex = p[3] - q[3], ey = p[4] - q[4], ez = p[5] - q[5];
+        const float lim = reach + q[9];
+        if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
+#pragma unroll
+        for (int la = 0; la < 3; ++la) {
+#pragma unroll
+          for (int ra = 0; ra < 3; ++ra) {
+            const float dx = p[la * 3] - q[ra * 3], dy = p[la * 3 + 1] - q[ra * 3 + 1], dz = p[la * 3 + 2] - q[ra * 3 + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < 16.f) {
+              const float d = sqrtf(d2);
+              const float g = 4.f - d;
+              const float sg = sqrtf(g);
+              const float dphi = -(1.5f * sg * d + g * sg) / (0.75f * d * d);
+              const float coef = -5.f * dphi / d;
+              fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
+            }
+          }
         }
       }
     }
   }
   block_sum3(fx, fy, fz, red);
-  const float inv = 1.f / (float)nl;
+  const float inv = 1.f / (float)(L * 3);
   fx *= inv; fy *= inv; fz *= inv;
   __syncthreads();
-  for (int l = tid; l < nl; l += 256) { x[l * 3] += fx; x[l * 3 + 1] += fy; x[l * 3 + 2] += fz; }
+  for (int l = tid; l < L * 3; l += 256) { x[l * 3] += fx; x[l * 3 + 1] += fy; x[l * 3 + 2] += fz; }
   if (tid == 0) { tr_update[b * 3] += fx; tr_update[b * 3 + 1] += fy; tr_update[b * 3 + 2] += fz; }
 }
 
