@@ -61,6 +61,9 @@ constexpr int MMA_REGS = 40;
 #ifndef EWS_ROW_INTERLEAVE
 #define EWS_ROW_INTERLEAVE 0   // (measured slower: 1.29 vs 1.21 ms) producer warp w builds slots {w&7, (w&7)+8, ...} of its residue instead of 8 consecutive slots:
 #endif                         // every warp gets the same mix of kNN slots (two table gathers) and far slots (one)
+#ifndef EWS_PIN_ADDR
+#define EWS_PIN_ADDR 0
+#endif
 #ifndef EWS_EPI_V3
 #define EWS_EPI_V3 1      // epilogue on tcgen05.ld.16x256b fragments: a thread holds 4 rows x 16 column pairs, so the gated
 #endif                    // segment sum is mostly in-thread FMAs (14 shuffle steps instead of 63)
@@ -291,8 +294,10 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         const int pr = (tid >> 6) * 64 + 4 * (tid & 15) + ((tid >> 4) & 3);
         const __half2 b = __floats2half2_rn(0.5f * p.b2[2 * pr], 0.5f * p.b2[2 * pr + 1]);
         const __half2 w = __floats2half2_rn(p.wa[2 * pr], p.wa[2 * pr + 1]);
-        reinterpret_cast<__half2*>(smem + OFF_VEC32)[tid] = b;
-        reinterpret_cast<__half2*>(smem + OFF_VEC32)[128 + tid] = w;
+        // 20-word stride per (ch, t%4) row: the four rows a quarter-warp reads land in disjoint bank groups
+        const int slot = (tid >> 4) * 20 + (tid & 15);
+        reinterpret_cast<__half2*>(smem + OFF_VEC32)[slot] = b;
+        reinterpret_cast<__half2*>(smem + OFF_VEC32)[160 + slot] = w;
       }
 #else
       reinterpret_cast<float*>(smem + OFF_VEC32)[tid] = 0.5f * p.b2[tid];
@@ -336,8 +341,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     // B_j is already in the S tile (loader warps, cp.async); this role gathers the two table rows of each edge into
     // registers one K block ahead (two buffers), forms u/2, applies SiLU and overwrites the 16-byte chunk in place.
     struct GBuf { uint4 td[2], to[2]; uint4 a; };
-    const uint32_t mring_s = sbase + OFF_META + (uint32_t)warp * 256u;      // shared-space address of this warp's ring
-    const uint32_t vwr_s = sbase + OFF_VEC + 1024u + (uint32_t)c8 * 16u;
+    uint32_t mring_s = sbase + OFF_META + (uint32_t)warp * 256u;      // shared-space address of this warp's ring
+    uint32_t vwr_s = sbase + OFF_VEC + 1024u + (uint32_t)c8 * 16u;
     // swizzled byte offset of this lane's chunk in row r0 + 4 i of a K block: (r0 + 4 i) * 128 + ((c8 ^ (r & 7)) << 4)
     uint32_t soff[2];
 #pragma unroll
@@ -345,6 +350,11 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const int r = prow(rsub + 4 * i);
       soff[i] = sbase + OFF_S + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
     }
+#if EWS_PIN_ADDR
+    // opaque to the compiler: keeps these four addresses in registers instead of re-deriving them from %tid and the
+    // shared window base in every K block (ptxas otherwise rematerialises ~25 instructions per K block)
+    asm volatile("" : "+r"(soff[0]), "+r"(soff[1]), "+r"(mring_s), "+r"(vwr_s));
+#endif
     auto issue = [&](GBuf& g, uint32_t mslot, size_t aoff, int kb) {
       const int colh = kb * 64 + c8 * 8;
       g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
@@ -536,7 +546,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     // Fragment layout: lane t = (rg = t >> 2, cq = t & 3) holds rows rr(k) = q*32 + rg + 8 k (k = 0..3) and, for every
     // 8-column block j = 0..15 of this warp's column half, the column pair 8 j + 2 cq + {0, 1}: m[k * 16 + j].
     const int rg = lane >> 2, cq = lane & 3;
-    const uint32_t vx_s = sbase + OFF_VEC32 + (uint32_t)((ch * 4 + cq) * 16) * 4u;
+    const uint32_t vx_s = sbase + OFF_VEC32 + (uint32_t)((ch * 4 + cq) * 20) * 4u;
     const uint32_t part_row_s = sbase + OFF_PART + (uint32_t)(q * 32 + rg) * 4u;      // + 32 k bytes for row k
     (void)erow; (void)vec_s; (void)vec32_s; (void)part_s;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
@@ -549,34 +559,40 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       float dot[4] = {0.f, 0.f, 0.f, 0.f};
       {
         uint32_t accA[8], accB[8];
-        uint32_t dA = 0, dB = 0;
+        uint32_t dA[2] = {0, 0}, dB[2] = {0, 0};
         uint4 bb = make_uint4(0, 0, 0, 0), ww = make_uint4(0, 0, 0, 0);
-        tmem_ld16x256_x2_issue(tbase, accA);
+        // iteration n = g * 4 + hh * 2 + half: column group g (blocks 4 g .. 4 g + 3: one LDS.128 of b2 / wa serves both
+        // row halves), row half hh (rows k = 2 hh, 2 hh + 1), blocks 2 jj, 2 jj + 1 with jj = 2 g + half
+        auto frag_addr = [&](int n) -> uint32_t {
+          const int g = n >> 2, hh = (n >> 1) & 1, jj = 2 * g + (n & 1);
+          return tbase + ((uint32_t)(hh * 16) << 16) + (uint32_t)(jj * 16);
+        };
+        tmem_ld16x256_x2_issue(frag_addr(0), accA);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {          // n = hh * 8 + jj: row half hh (rows k = 2 hh, 2 hh + 1), blocks 2 jj, 2 jj + 1
-          const int hh = n >> 3, jj = n & 7;
+        for (int n = 0; n < 16; ++n) {
+          const int g = n >> 2, hh = (n >> 1) & 1, half = n & 1, jj = 2 * g + half;
           uint32_t* cur = (n & 1) ? accB : accA;
           uint32_t* nxt = (n & 1) ? accA : accB;
           tmem_ld_wait8(cur);
-          if (n + 1 < 16) tmem_ld16x256_x2_issue(tbase + ((uint32_t)(((n + 1) >> 3) * 16) << 16) + (uint32_t)(((n + 1) & 7) * 16), nxt);
-          if ((jj & 1) == 0) {
-            bb = lds128(vx_s + (uint32_t)(jj >> 1) * 16u);
-            ww = lds128(vx_s + 512u + (uint32_t)(jj >> 1) * 16u);
+          if (n + 1 < 16) tmem_ld16x256_x2_issue(frag_addr(n + 1), nxt);
+          if ((n & 3) == 0) {
+            bb = lds128(vx_s + (uint32_t)g * 16u);
+            ww = lds128(vx_s + 640u + (uint32_t)g * 16u);
           }
-          const uint32_t b0 = (jj & 1) ? bb.z : bb.x, b1 = (jj & 1) ? bb.w : bb.y;
-          const uint32_t w0 = (jj & 1) ? ww.z : ww.x, w1 = (jj & 1) ? ww.w : ww.y;
+          const uint32_t b0 = half ? bb.z : bb.x, b1 = half ? bb.w : bb.y;
+          const uint32_t w0 = half ? ww.z : ww.x, w1 = half ? ww.w : ww.y;
           const uint32_t x00 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), b0));
           const uint32_t x10 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), b0));
           const uint32_t x01 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), b1));
           const uint32_t x11 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), b1));
           m[(2 * hh) * 16 + 2 * jj] = x00; m[(2 * hh) * 16 + 2 * jj + 1] = x01;
           m[(2 * hh + 1) * 16 + 2 * jj] = x10; m[(2 * hh + 1) * 16 + 2 * jj + 1] = x11;
-          dA = h2fma(x00, w0, dA); dA = h2fma(x01, w1, dA);
-          dB = h2fma(x10, w0, dB); dB = h2fma(x11, w1, dB);
-          if ((jj & 3) == 3) {      // 8 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
-            const float2 fa = h2f2(dA), fb = h2f2(dB);
+          dA[hh] = h2fma(x00, w0, dA[hh]); dA[hh] = h2fma(x01, w1, dA[hh]);
+          dB[hh] = h2fma(x10, w0, dB[hh]); dB[hh] = h2fma(x11, w1, dB[hh]);
+          if ((g & 1) && half) {    // 8 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
+            const float2 fa = h2f2(dA[hh]), fb = h2f2(dB[hh]);
             dot[2 * hh] += fa.x + fa.y; dot[2 * hh + 1] += fb.x + fb.y;
-            dA = dB = 0;
+            dA[hh] = dB[hh] = 0;
           }
         }
       }
