@@ -315,7 +315,7 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
   const int N = ctx->N, M = B * N;
   int rc;
   if ((rc = launch_prepare(ctx, B, lig_pos, ws, s))) return rc;
-  if ((rc = launch_graph(ctx, B, edges, exp_noise, seed, stream_base, fwd_index, ws, s))) return rc;
+  if ((rc = launch_graph(ctx, B, (flags & DFM_GRAPH_GENERIC) != 0, edges, exp_noise, seed, stream_base, fwd_index, ws, s))) return rc;
   if (edges_out) {
     CUDA_TRY(cudaMemcpy2DAsync(edges_out, sizeof(int32_t) * ctx->K, ws.nbr, sizeof(int32_t) * SLOTS,
                                sizeof(int32_t) * ctx->K, (size_t)M, cudaMemcpyDeviceToDevice, s));
@@ -487,7 +487,7 @@ extern "C" int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_st
   float* tbuf = ws.tsc + (size_t)B * 7;   // [B] time values live in the tail of the scratch block
   float* trs = ws.tsc;
   float* rots = ws.tsc + (size_t)B * 4;
-  const uint32_t fflags = flags & DFM_PRECISION_FP32;
+  const uint32_t fflags = flags & (DFM_PRECISION_FP32 | DFM_GRAPH_GENERIC);
   for (int i = 0; i < num_steps; ++i) {
     const bool last = i == num_steps - 1;
     k_fill<<<(B + 255) / 256, 256, 0, s>>>(tbuf, ts[i], B);

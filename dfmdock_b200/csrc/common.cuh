@@ -201,7 +201,7 @@ int launch_coord_tc(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, __half* agg16, cudaStream_t s);
 
 int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s);
-int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
+int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const float* exp_noise, uint64_t seed,
                  uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s);
 int launch_broadcast_h0(dfm_ctx* ctx, int B, Workspace& ws, cudaStream_t s);
 int launch_graphnorm_silu(dfm_ctx* ctx, int B, int layer, Workspace& ws, cudaStream_t s);
@@ -244,7 +244,10 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform on the OPEN interval (0, 1): 23 random bits + 1/2, every value exactly representable, so neither 0 nor 1 can be
+// returned (with 24 bits the top value rounds to 1.0f and -logf gives -0.0f, which the bit-pattern selection of
+// k_graph_sel orders last while the float comparison of k_graph orders it first -- found by the kernel-equivalence test)
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 // kinds of draws (third counter word, high byte)
 #define RNG_EDGE 0u
 #define RNG_STEP 1u

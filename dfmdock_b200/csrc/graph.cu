@@ -433,14 +433,14 @@ static int launch_graph_sel(dfm_ctx* ctx, int B, const float* exp_noise, uint64_
   return 0;
 }
 
-int launch_graph(dfm_ctx* ctx, int B, const int32_t* edges, const float* exp_noise, uint64_t seed,
+int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const float* exp_noise, uint64_t seed,
                  uint64_t stream_base, uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
   constexpr int WARPS = 8;
   const int N = ctx->N;
   // register-resident selection for the common sizes (no injected edge table); larger complexes use the smem kernel
   static int use_sel = -1;
   if (use_sel < 0) { const char* e = getenv("DFM_GRAPH_KERNEL"); use_sel = e ? atoi(e) : 1; }
-  if (use_sel && edges == nullptr && N >= 2) {
+  if (use_sel && !generic && edges == nullptr && N >= 2) {
     if (N <= 320) return launch_graph_sel<10>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
     if (N <= 512) return launch_graph_sel<16>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
     if (N <= 1024) return launch_graph_sel<32>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);

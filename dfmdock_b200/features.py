@@ -28,16 +28,19 @@ def get_position_matrix(n_rec, n_lig, width=66, sym=0.0):
     return pm
 
 
-def batch_from_record(rec, pos_width=66):
-    """rec = {"receptor": {x[n,1280], pos[n,3,3], seq}, "ligand": {...}} -> batch dict (CPU tensors)."""
+def batch_from_record(rec, pos_width=66, with_position_matrix=True):
+    """rec = {"receptor": {x[n,1280], pos[n,3,3], seq}, "ligand": {...}} -> batch dict (CPU tensors).
+
+    with_position_matrix=False leaves out the dense [N,N,P] one-hot (1.7 GB for the 2548-residue db5 complex): the CUDA
+    library rebuilds relpos from (i, j, R) anyway and only needs the homomer flag, passed as batch["sym"]."""
     r, l = rec["receptor"], rec["ligand"]
     rec_x = torch.cat([r["x"].float(), sequence_to_onehot(r["seq"])], dim=-1)
     lig_x = torch.cat([l["x"].float(), sequence_to_onehot(l["seq"])], dim=-1)
     sym = 1.0 if r["seq"] == l["seq"] else 0.0
-    return {
-        "rec_x": rec_x, "lig_x": lig_x, "rec_pos": r["pos"].float(), "lig_pos": l["pos"].float(),
-        "position_matrix": get_position_matrix(rec_x.shape[0], lig_x.shape[0], pos_width, sym),
-    }
+    batch = {"rec_x": rec_x, "lig_x": lig_x, "rec_pos": r["pos"].float(), "lig_pos": l["pos"].float(), "sym": sym}
+    if with_position_matrix:
+        batch["position_matrix"] = get_position_matrix(rec_x.shape[0], lig_x.shape[0], pos_width, sym)
+    return batch
 
 
 def synthetic_complex(n_rec, n_lig, seed=0, x_dim=1301, pos_width=66):

@@ -41,7 +41,7 @@ from . import pdbio
 from .checkpoint import load_db5_record
 from .features import batch_from_record
 from .metrics import KEYS as METRIC_KEYS, compute_metrics_batch
-from .sampler import Euler_Maruyama_sampler, sample_trajectories
+from .sampler import Euler_Maruyama_sampler, sample_complex_set, sample_trajectories
 from .score_model import Score_Model
 
 THREE = {"A": "ALA", "R": "ARG", "N": "ASN", "D": "ASP", "C": "CYS", "Q": "GLN", "E": "GLU", "G": "GLY", "H": "HIS",
@@ -61,7 +61,7 @@ def set_seed(seed):
 STRUCTURE_EXT = (".pdb", ".ent")
 
 
-def load_inputs(path_1, path_2=None, id=None, embedder=None):
+def load_inputs(path_1, path_2=None, id=None, embedder=None, parse_only=False):
     """-> inputs dict {"id", "receptor": {x, pos, seq[, structure, aa_coords, bb_coords]}, "ligand": {...}}.
 
     path_1 alone: a two-chain record (data/db5_test/<id>.pt layout).  path_1 + path_2: one single-chain record each
@@ -72,6 +72,8 @@ def load_inputs(path_1, path_2=None, id=None, embedder=None):
     if any(is_pdb):
         if not all(is_pdb):
             raise ValueError("give either two PDB files or pre-embedded records, not a mix: %s, %s" % (path_1, path_2))
+        if parse_only:
+            return pdbio.record_from_pdbs(path_1, path_2, None, id=id)
         if embedder is None:
             raise RuntimeError(
                 "%s: raw structure files need ESM-2 650M embeddings (src/inference_base.py:294-306).  Pass --esm_dir with a local "
@@ -183,10 +185,16 @@ def run(args, model, inputs, batch, device):
                                   centre_mode=centre_mode, seed=args.seed, gather_poses=True, ode=ode)
         poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
                   int(res["num_clashes"][i])) for i in range(args.num_samples)]
+    return finish_samples(args, inputs, batch["rec_pos"], native_rec, native_lig, poses, frames, centre_mode, device)
+
+
+def finish_samples(args, inputs, rec_pos, native_rec, native_lig, poses, frames, centre_mode, device):
+    """Metric rows of every sample + (rank 0) the structure / trajectory files."""
+    trj_dir = getattr(args, "out_trj_dir", None)
+    rows = []
     # metrics of every pose in one launch (src/inference.py:393 calls compute_metrics per sample); the native pose is the
     # one in the input record unless --native_dir is given, like the reference's `native = inputs[...]['bb_coords']`
-    met = compute_metrics_batch(batch["rec_pos"], torch.stack([p[0] for p in poses]), native_rec, native_lig,
-                                device=device).cpu()
+    met = compute_metrics_batch(rec_pos, torch.stack([p[0] for p in poses]), native_rec, native_lig, device=device).cpu()
     for i, (lig_pos, rot_u, tr_u, energy, clashes) in enumerate(poses):
         row = {"id": inputs["id"], "index": str(i)}
         row.update({k: (round(float(met[i, j]), 6) if k == "fnat" else float(met[i, j])) for j, k in enumerate(METRIC_KEYS)})
@@ -195,12 +203,49 @@ def run(args, model, inputs, batch, device):
         rows.append(row)
     if _rank() == 0:
         if getattr(args, "out_dir", None):
-            write_samples(args.out_dir, inputs, batch, poses, centre_mode, device)
+            write_samples(args.out_dir, inputs, {"rec_pos": rec_pos}, poses, centre_mode, device)
         if trj_dir and frames:
             os.makedirs(trj_dir, exist_ok=True)
             for i, trj in enumerate(frames):
-                pdbio.write_trajectory_pdb(os.path.join(trj_dir, "%s_p%d.pdb" % (inputs["id"], i)), batch["rec_pos"], trj,
+                pdbio.write_trajectory_pdb(os.path.join(trj_dir, "%s_p%d.pdb" % (inputs["id"], i)), rec_pos, trj,
                                            inputs["receptor"]["seq"], inputs["ligand"]["seq"])
+    return rows
+
+
+def run_planned(args, model, paths_list, embedder, device):
+    """Many complexes under torchrun (BASELINE config #5): (complex, trajectory) work items planned over the ranks
+    (dfmdock_b200.distributed.plan_work), one object all-gather at the end, rank 0 computes the metrics and writes."""
+    centre_mode = int(getattr(args, "centre_mode", 1))
+    light = [load_inputs(p1, p2, id=id, parse_only=True) for id, p1, p2 in paths_list]
+    sizes = [len(r["receptor"]["seq"]) + len(r["ligand"]["seq"]) for r in light]
+
+    def loader(c):
+        def load():
+            rec = light[c]
+            if rec["receptor"].get("x") is None or rec["ligand"].get("x") is None:
+                if embedder is None:
+                    raise RuntimeError("%s: raw structure files need ESM-2 embeddings: pass --esm_dir" % paths_list[c][1])
+                pdbio.embed_record(rec, embedder)
+            return batch_from_record(rec, pos_width=model.pos_width, with_position_matrix=False)
+        return load
+
+    results, plan = sample_complex_set(
+        model, [loader(c) for c in range(len(light))], sizes, args.num_samples, num_steps=args.num_steps,
+        use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing, tr_noise_scale=args.tr_noise_scale,
+        rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode, seed=args.seed, ode=bool(getattr(args, "ode", False)))
+    rows = []
+    if _rank() == 0:
+        for c, res in enumerate(results):
+            inputs = light[c]
+            rec_pos, lig0 = inputs["receptor"]["pos"].float(), inputs["ligand"]["pos"].float()
+            if getattr(args, "native_dir", None):
+                nat = pdbio.get_native(os.path.join(args.native_dir, "%s.pdb" % inputs["id"]))
+                native_rec, native_lig = nat[0], nat[1]
+            else:
+                native_rec, native_lig = rec_pos, lig0
+            poses = [(res["lig_pos"][i], res["rot_update"][i], res["tr_update"][i], float(res["energy"][i]),
+                      int(res["num_clashes"][i])) for i in range(args.num_samples)]
+            rows.extend(finish_samples(args, inputs, rec_pos, native_rec, native_lig, poses, None, centre_mode, device))
     return rows
 
 
@@ -240,8 +285,11 @@ def main(args, embedder=None):
     model.to(device).eval()
     if embedder is None and getattr(args, "esm_dir", None):
         embedder = pdbio.EsmEmbedder(args.esm_dir, device=device)
-    results = []
-    for id, p1, p2 in paths_list:
+    world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+    planned = (world > 1 and len(paths_list) > 1 and not getattr(args, "reference_rng", False)
+               and not getattr(args, "out_trj_dir", None) and not getattr(args, "get_gt_energy", False))
+    results = run_planned(args, model, paths_list, embedder, device) if planned else []
+    for id, p1, p2 in ([] if planned else paths_list):
         inputs = load_inputs(p1, p2, id=id, embedder=embedder)
         batch = batch_from_record(inputs, pos_width=model.pos_width)
         results.extend(run(args, model, inputs, batch, device))

@@ -284,14 +284,24 @@ class EsmEmbedder:
         return out[0, 1:-1, :].float().cpu()
 
 
+def embed_record(rec, embedder):
+    """Adds the ESM-2 rows "x" to the chains of a record that does not have them yet (in place)."""
+    for key in ("receptor", "ligand"):
+        info = rec[key]
+        if info.get("x") is None:
+            x = embedder(info["seq"])
+            if x.shape[0] != len(info["seq"]):
+                raise ValueError("%s: embedder returned %d rows for %d residues" % (key, x.shape[0], len(info["seq"])))
+            info["x"] = x
+    return rec
+
+
 def record_from_pdbs(pdb_1, pdb_2, embedder, id=None):
-    """Two raw PDB files -> the input record batch_from_record consumes (+ the structures for all-atom output)."""
+    """Two raw PDB files -> the input record batch_from_record consumes (+ the structures for all-atom output).
+    embedder=None parses only (sizes, sequences, structures); embed_record() completes the record later."""
     out = {"id": id or os.path.splitext(os.path.basename(str(pdb_1)))[0]}
     for key, path in (("receptor", pdb_1), ("ligand", pdb_2)):
         info = get_info_from_pdb(path)
-        x = embedder(info["seq"])
-        if x.shape[0] != len(info["seq"]):
-            raise ValueError("%s: embedder returned %d rows for %d residues" % (path, x.shape[0], len(info["seq"])))
-        info.update({"x": x, "pos": torch.from_numpy(info["bb_coords"]).float()})
+        info.update({"x": None, "pos": torch.from_numpy(info["bb_coords"]).float()})
         out[key] = info
-    return out
+    return embed_record(out, embedder) if embedder is not None else out

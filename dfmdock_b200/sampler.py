@@ -102,3 +102,43 @@ def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_c
         out["lig_pos"] = dist_utils.gather_rows(local["lig_pos"].reshape(hi - lo, -1), num_samples, group).view(-1, L, 3, 3)
     out["best"] = int(torch.argmin(out["energy"]).item()) if num_samples > 0 else -1
     return out
+
+
+def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-3, use_clash_force=False,
+                       noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, seed=0, ode=False,
+                       group=None, min_nodes=8192):
+    """Many complexes x num_samples trajectories each (BASELINE config #5) over the ranks of `group`.
+
+    loaders[c]() -> batch dict of complex c (called only on the ranks that own a chunk of it); sizes[c] = residues of
+    complex c (for the plan, dfmdock_b200.distributed.plan_work).  Trajectory k of every complex uses Philox subsequence
+    k whatever the plan, so the result does not depend on the number of ranks.  One collective at the end: the chunks'
+    result rows (pose, rot_update, tr_update, energy, num_clashes) are all-gathered as objects.
+    Returns (results, plan): results[c] = dict of CPU tensors {lig_pos [T,L,3,3], rot_update [T,3], tr_update [T,3],
+    energy [T], num_clashes [T], best} on every rank.
+    """
+    rank, world = dist_utils.rank_world(group)
+    plan = dist_utils.plan_work(sizes, num_samples, world, min_nodes=min_nodes)
+    mine = {}
+    for c, lo, hi, r in plan:
+        if r == rank:
+            mine.setdefault(c, []).append((lo, hi))
+    done = []
+    for c in sorted(mine):
+        batch = loaders[c]()
+        model.set_complex(batch)
+        for lo, hi in mine[c]:
+            res = model.sample(batch["lig_pos"], hi - lo, num_steps=num_steps, eps=eps, tr_noise_scale=tr_noise_scale,
+                               rot_noise_scale=rot_noise_scale, use_clash_force=use_clash_force,
+                               noise_annealing=noise_annealing, centre_mode=centre_mode, seed=seed, stream_base=lo, ode=ode)
+            done.append((c, lo, hi, {k: v.cpu() for k, v in res.items()}))
+    everything = [item for part in dist_utils.gather_objects(done, group) for item in part]
+    results = []
+    for c in range(len(sizes)):
+        parts = sorted((lo, hi, d) for cc, lo, hi, d in everything if cc == c)
+        covered = [(lo, hi) for lo, hi, _ in parts]
+        if not parts or covered[0][0] != 0 or covered[-1][1] != num_samples or any(a[1] != b[0] for a, b in zip(covered, covered[1:])):
+            raise RuntimeError("sample_complex_set: complex %d is not covered exactly once: %s" % (c, covered))
+        out = {k: torch.cat([d[k] for _, _, d in parts], dim=0) for k in parts[0][2]}
+        out["best"] = int(torch.argmin(out["energy"]).item())
+        results.append(out)
+    return results, plan

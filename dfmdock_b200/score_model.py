@@ -32,6 +32,7 @@ class Score_Model:
         self.cut_off = float(hparams["model"].get("cut_off", 20.0))
         self.pos_width = int(self.state_dict_cpu["positional_embed.weight"].shape[1])
         self.precision = precision          # "fp16" (tcgen05, default) or "fp32" (FFMA parity mode)
+        self.graph_generic = False          # True: always build the graph with the generic kernel (the N > 1024 path)
         self.edge_rng = "torch"             # forward(batch): "torch" = reference-style global RNG, "philox" = in-kernel
         self.device = None
         self._ctx = None
@@ -122,7 +123,7 @@ class Score_Model:
         rx = rec_x.to(dev, torch.float32).contiguous()
         lx = lig_x.to(dev, torch.float32).contiguous()
         R, L = rx.shape[0], lx.shape[0]
-        sym = 0.0
+        sym = float(batch.get("sym", 0.0)) if self.pos_width == 67 else 0.0
         pm = batch.get("position_matrix")
         if pm is not None:
             if pm.shape[-1] == 67:
@@ -169,6 +170,8 @@ class Score_Model:
             f |= _lib.CENTRE_ALL_ATOMS
         if kw.get("ode"):
             f |= _lib.ODE
+        if kw.get("graph_generic") or self.graph_generic:
+            f |= _lib.GRAPH_GENERIC
         return f
 
     # ---- batched operators ---------------------------------------------------------------------------

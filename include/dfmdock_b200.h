@@ -48,7 +48,9 @@ enum {
   DFM_CLASH_FORCE = 1u << 2,   /* inference.py:358-361 soft-clash translation after every step */
   DFM_NOISE_ANNEAL = 1u << 3,  /* noise_scale = t (inference_base.py:428-430) */
   DFM_CENTRE_ALL_ATOMS = 1u << 4, /* rotate about the N/CA/C centroid (inference.py:224-245) instead of the CA centroid (inference_base.py:322-343) */
-  DFM_ODE = 1u << 5            /* probability-flow ODE branch of torch_reverse (so3_diffuser.py:366-367) */
+  DFM_ODE = 1u << 5,           /* probability-flow ODE branch of torch_reverse (so3_diffuser.py:366-367) */
+  DFM_GRAPH_GENERIC = 1u << 6  /* build the stochastic graph with the generic (shared-memory) kernel that complexes of more than
+                                  1024 residues use, whatever the size: same neighbours as the register-resident kernels (test knob) */
 };
 
 /* Fixed architecture of the shipped checkpoints (configs/model/score_model_mlsb.yaml). */

@@ -22,7 +22,7 @@ from dfmdock_b200 import Score_Model  # noqa: E402
 from dfmdock_b200.features import batch_from_record  # noqa: E402
 from dfmdock_b200.inference import init_distributed  # noqa: E402
 from dfmdock_b200.metrics import KEYS, compute_metrics_batch  # noqa: E402
-from dfmdock_b200.sampler import sample_trajectories  # noqa: E402
+from dfmdock_b200.sampler import sample_complex_set  # noqa: E402
 
 T, S = int(os.environ.get("C5_SAMPLES", "40")), int(os.environ.get("C5_STEPS", "40"))
 
@@ -35,42 +35,52 @@ def main():
     ck = torch.load(os.path.join(ref, "pinder_0.pt"), weights_only=False)
     model = Score_Model(ck["state_dict"], ck["hparams"], precision="fp16").to(dev)
     paths = sorted(glob.glob(os.path.join(ref, "db5_all", "*.pt"))) or sorted(glob.glob(os.path.join(ref, "db5_*.pt")))
-    rows, total_ms, total_ps = [], 0.0, 0
-    # warm-up (allocator, module load) on the first complex
-    b0 = batch_from_record(torch.load(paths[0], weights_only=False), pos_width=model.pos_width)
-    sample_trajectories(model, b0, max(world, 2), num_steps=3, use_clash_force=True, centre_mode=1, seed=1)
+    ids = [os.path.splitext(os.path.basename(p))[0].replace("db5_", "") for p in paths]
+    recs = [torch.load(p, weights_only=False) for p in paths]
+    sizes = [r["receptor"]["pos"].shape[0] + r["ligand"]["pos"].shape[0] for r in recs]
+    loaders = [(lambda r=r: batch_from_record(r, pos_width=model.pos_width, with_position_matrix=False)) for r in recs]
+    # warm-up (allocator, module load) on the smallest complex
+    b0 = loaders[min(range(len(sizes)), key=lambda c: sizes[c])]()
+    model.set_complex(b0)
+    model.sample(b0["lig_pos"], 2, num_steps=3, use_clash_force=True, centre_mode=1, seed=1)
     torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
     wall0 = time.perf_counter()
-    for p in paths:
-        cid = os.path.splitext(os.path.basename(p))[0].replace("db5_", "")
-        batch = batch_from_record(torch.load(p, weights_only=False), pos_width=model.pos_width)
-        R, L = batch["rec_pos"].shape[0], batch["lig_pos"].shape[0]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        res = sample_trajectories(model, batch, T, num_steps=S, use_clash_force=True, centre_mode=1, seed=42, gather_poses=True)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        ms = float(ms)
-        met = compute_metrics_batch(batch["rec_pos"], res["lig_pos"], batch["rec_pos"], batch["lig_pos"], device=dev).cpu()
-        best = res["best"]
-        total_ms += ms
-        total_ps += T * S
-        row = {"id": cid, "index": str(best), "n_rec": R, "n_lig": L}
-        row.update({k: float(met[best, j]) for j, k in enumerate(KEYS)})
-        row.update({"energy": float(res["energy"][best]), "num_clashes": int(res["num_clashes"][best]), "ms": ms,
-                    "best_dockq_of_40": float(torch.nan_to_num(met[:, 4], nan=0.0).max())})
-        rows.append(row)
-        if rank == 0:
-            print("%-5s R=%4d L=%4d  %8.1f ms  %7.0f pose-steps/s  lowest energy %8.2f (sample %2d: DockQ %.3f, L-RMSD %6.2f)  best DockQ of %d: %.3f"
-                  % (cid, R, L, ms, T * S / (ms * 1e-3), row["energy"], best, row["DockQ"], row["l_rmsd"], T, row["best_dockq_of_40"]), flush=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    results, plan = sample_complex_set(model, loaders, sizes, T, num_steps=S, use_clash_force=True, centre_mode=1, seed=42)
+    e1.record()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    mine = sum(1 for ch in plan if ch[3] == rank)
+    # device-side busy time of this rank's own chunks is not separable from the final object gather, so report both the
+    # whole call (max over ranks) and the wall clock
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms)
     if rank == 0:
-        print("c5 total: %d complexes x %d traj x %d steps on %d GPU(s): sampling %.2f s (device time, max over ranks), wall %.2f s incl. "
-              "H2D of the records and metrics; %.0f pose-steps/s" % (len(rows), T, S, world, total_ms * 1e-3, wall, total_ps / (total_ms * 1e-3)))
+        rows = []
+        for c, res in enumerate(results):
+            rec = recs[c]
+            rec_pos, lig0 = rec["receptor"]["pos"].float(), rec["ligand"]["pos"].float()
+            met = compute_metrics_batch(rec_pos, res["lig_pos"], rec_pos, lig0, device=dev).cpu()
+            best = res["best"]
+            row = {"id": ids[c], "index": str(best), "n_rec": rec_pos.shape[0], "n_lig": lig0.shape[0]}
+            row.update({k: float(met[best, j]) for j, k in enumerate(KEYS)})
+            row.update({"energy": float(res["energy"][best]), "num_clashes": int(res["num_clashes"][best]),
+                        "best_dockq_of_40": float(torch.nan_to_num(met[:, 4], nan=0.0).max()),
+                        "chunks": " ".join("%d-%d@%d" % (lo, hi, r) for cc, lo, hi, r in plan if cc == c),
+                        "energy_checksum": "%.6f" % float(res["energy"].double().sum())})
+            rows.append(row)
+            print("%-5s R=%4d L=%4d  lowest energy %8.2f (sample %2d: DockQ %.3f, L-RMSD %6.2f)  best DockQ of %d: %.3f  chunks %s"
+                  % (ids[c], row["n_rec"], row["n_lig"], row["energy"], best, row["DockQ"], row["l_rmsd"], T, row["best_dockq_of_40"],
+                     row["chunks"]), flush=True)
+        total_ps = len(rows) * T * S
+        print("c5 total: %d complexes x %d traj x %d steps on %d GPU(s), %d chunks (%d on rank 0): %.2f s device time (max over ranks, "
+              "incl. H2D of the records and the final gather), wall %.2f s; %.0f pose-steps/s"
+              % (len(rows), T, S, world, len(plan), mine, ms * 1e-3, wall, total_ps / (ms * 1e-3)))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "db5_c5_%dgpu.csv" % world), "w", newline="") as f:
             w = csv.DictWriter(f, fieldnames=list(rows[0].keys()))

@@ -105,6 +105,67 @@ def test_philox_graph_properties():
     assert float(samp_d) < float(dm[mask].mean())
 
 
+def test_generic_graph_kernel_equals_register_resident_kernels():
+    """Complexes of more than 1024 residues build their graph with the generic shared-memory kernel; DFM_GRAPH_GENERIC forces
+    it at any size.  Same Philox draws / same injected Exp(1) noise -> the same neighbour table (integer work: exact)."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd, hp = synthetic_state_dict(0, 66), synthetic_hparams(66)
+    for n_rec, n_lig in ((40, 30), (150, 150), (300, 260), (600, 300)):      # S = 10, 10, 32, 32 keys per lane
+        batch = synthetic_complex(n_rec, n_lig, seed=2)
+        batch["lig_pos"] = batch["lig_pos"] - torch.tensor([12.0, 0.0, 0.0])
+        model = _model(sd, hp, "fp16")
+        model.set_complex(batch)
+        lig = batch["lig_pos"][None].repeat(2, 1, 1, 1)
+        t = torch.full((2,), 0.4)
+        a = model.score(lig, t, seed=3, stream_base=7, forward_index=5, return_edges=True)
+        model.graph_generic = True
+        b = model.score(lig, t, seed=3, stream_base=7, forward_index=5, return_edges=True)
+        ea, eb = a["edges"].cpu().long(), b["edges"].cpu().long()
+        assert torch.equal(ea[:, :, :20].sort(-1).values, eb[:, :, :20].sort(-1).values), (n_rec, n_lig)
+        assert torch.equal(ea[:, :, 20:].sort(-1).values, eb[:, :, 20:].sort(-1).values), (n_rec, n_lig)
+        # and the scores computed on those graphs agree (slot order inside a block may differ: fp16 summation order)
+        assert rel_err(a["f"].cpu(), b["f"].cpu()) <= 5e-3
+        model.graph_generic = False
+    # injected Exp(1) noise goes through both kernels as well
+    sd, hp, batch = case_small()
+    model = _model(sd, hp, "fp32")
+    model.set_complex(batch)
+    item = load_golden("fwd_synth_n70.pt")[0]
+    a = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), exp_noise=item["exp"][None], return_edges=True)["edges"]
+    model.graph_generic = True
+    b = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), exp_noise=item["exp"][None], return_edges=True)["edges"]
+    assert torch.equal(a[0, :, :20].sort(-1).values, b[0, :, :20].sort(-1).values)
+    assert torch.equal(a[0, :, 20:].sort(-1).values, b[0, :, 20:].sort(-1).values)
+
+
+def test_large_complex_beyond_1024_residues():
+    """N = 1300 (> 1024: generic graph kernel, the 1N2C regime): kNN block equals the exact 20 nearest residues, 60 distinct
+    neighbours per residue, finite scores, batched == single."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd, hp = synthetic_state_dict(0, 66), synthetic_hparams(66)
+    batch = synthetic_complex(800, 500, seed=6)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([10.0, 0.0, 0.0])
+    model = _model(sd, hp, "fp16")
+    model.set_complex(batch)
+    lig = batch["lig_pos"][None].repeat(2, 1, 1, 1)
+    o = model.score(lig, torch.full((2,), 0.5), seed=1, forward_index=0, want_energy=True, return_edges=True)
+    e = o["edges"][0].cpu().long()
+    N = e.shape[0]
+    pos = torch.cat([batch["rec_pos"], batch["lig_pos"]], 0)[:, 1].double()
+    d = (pos[:, None, :] - pos[None, :, :]).norm(dim=-1)
+    knn = torch.topk(d, 20, largest=False).indices
+    bad = int((e[:, :20].sort(1).values != knn.sort(1).values).any(dim=1).sum())
+    assert bad <= N // 100, bad                      # exact distance ties of the synthetic chain may flip the 20th neighbour
+    srt = e.sort(1).values
+    assert int((srt[:, 1:] == srt[:, :-1]).any(dim=1).sum()) == 0 and int(e.min()) >= 0 and int(e.max()) < N
+    assert torch.isfinite(o["f"]).all() and torch.isfinite(o["energy"]).all()
+    single = model.score(lig[1:], torch.full((1,), 0.5), seed=1, stream_base=1, forward_index=0, want_energy=True)
+    assert rel_err(single["f"].cpu()[0], o["f"].cpu()[1]) <= 1e-6
+    assert int(single["num_clashes"][0]) == int(o["num_clashes"][1])
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_batched_equals_single(precision):
     sd, hp, batch = case_small()

@@ -179,3 +179,72 @@ def test_inference_cli_surface_matches_reference_flags(tmp_path):
     assert lines[0][12:16].strip() == "N" and lines[0][17:20] == "ALA" and lines[0][21] == "A"
     assert abs(float(lines[1][30:38]) - float(b["rec_pos"][0, 1, 0])) < 1e-3
     assert inf.ligand_rmsd(b["lig_pos"], b["lig_pos"]) == 0.0
+
+
+def test_plan_work_covers_every_trajectory_once_and_balances():
+    """BASELINE config #5 planner: exact cover, deterministic, balanced, never more chunks than useful."""
+    from dfmdock_b200.distributed import complex_cost, plan_work
+    db5 = [395, 695, 343, 456, 575, 626, 561, 2548, 329, 197, 352, 320, 430, 377, 430, 382, 339, 628, 404, 240, 535, 373, 588, 492, 214]
+    for sizes, T in ((db5, 40), ([197], 40), ([300, 300, 300], 7), ([2548], 3), ([], 40)):
+        for world in (1, 2, 3, 8):
+            plan = plan_work(sizes, T, world)
+            assert plan == plan_work(sizes, T, world)
+            seen = {}
+            load = [0.0] * world
+            for c, lo, hi, r in plan:
+                assert 0 <= r < world and 0 <= lo < hi <= T
+                for k in range(lo, hi):
+                    assert (c, k) not in seen
+                    seen[(c, k)] = r
+                load[r] += complex_cost(sizes[c], T) * (hi - lo) / T
+            assert len(seen) == len(sizes) * T
+            for c, n in enumerate(sizes):
+                parts = [ch for ch in plan if ch[0] == c]
+                assert len(parts) <= max(1, min(world, T))
+                if len(parts) > 1:        # a complex is only cut when the pieces still fill a GPU
+                    assert min(hi - lo for _, lo, hi, _ in parts) * n >= 8192 // 2
+            if sizes is db5 and world > 1:
+                assert max(load) <= 1.15 * sum(load) / world, (world, load)
+    # small complexes stay whole: 40 trajectories x 197 residues is one launch-sized chunk
+    assert len(plan_work([197, 214, 240], 40, 8)) == 3
+
+
+_GLOO_SET_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DFM_ROOT"])
+from dfmdock_b200 import sampler
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["DFM_PORT"], rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+
+class FakeModel:                        # stands in for the CUDA model: result rows encode (complex, trajectory)
+    def set_complex(self, batch): self.c = batch["c"]
+    def sample(self, lig_pos0, n, stream_base=0, **kw):
+        k = torch.arange(stream_base, stream_base + n, dtype=torch.float32)
+        return {"lig_pos": (self.c * 1000 + k)[:, None, None, None].expand(n, 2, 3, 3).clone(), "rot_update": k[:, None].expand(n, 3).clone(),
+                "tr_update": k[:, None].expand(n, 3).clone(), "energy": -((k - 3 - self.c) ** 2), "num_clashes": torch.zeros(n, dtype=torch.int32)}
+
+sizes = [900, 200, 2500, 300]
+loaders = [(lambda c=c: {"c": c, "lig_pos": torch.zeros(2, 3, 3)}) for c in range(4)]
+results, plan = sampler.sample_complex_set(FakeModel(), loaders, sizes, 12, num_steps=2, min_nodes=2048)
+assert {r for _, _, _, r in plan} == {0, 1}, plan
+for c, res in enumerate(results):
+    assert res["lig_pos"].shape == (12, 2, 3, 3)
+    assert torch.equal(res["lig_pos"][:, 0, 0, 0], c * 1000 + torch.arange(12, dtype=torch.float32)), (c, res["lig_pos"][:, 0, 0, 0])
+    assert res["best"] == int(torch.argmin(res["energy"]))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_complex_set_sharding_over_gloo(tmp_path):
+    script = tmp_path / "worker_set.py"
+    script.write_text(_GLOO_SET_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), DFM_ROOT=ROOT, DFM_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
