@@ -322,7 +322,8 @@ def run_cuda(args):
             "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": "synthetic 2x150-residue complex (BASELINE config #3), %d trajectories per GPU in lock step" % B,
                        "n_res": N, "trajectories_per_gpu": B, "edges_per_step_per_gpu": 60 * N * B,
-                       "weights": "random-init, shipped architecture (H=256, depth 6)",
+                       "weights": "random-init, shipped architecture (H=256, depth 6); the scores are not physical, so the poses drift "
+                                  "apart and the final energy head sees no pair inside its 20 A cut-off (full_job.best_energy = 0)",
                        "l2": "per-step working set ~%.1f GB per GPU, far larger than the 126 MB L2; no explicit flush" % (1.9),
                        "parallelism": "trajectory-sharded x%d, one all-gather of [T,8] at the end" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * L * 36 + B * 4, "d2h_bytes_per_step": B * L * 36 + B * 24,

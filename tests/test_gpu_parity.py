@@ -417,26 +417,34 @@ def test_inference_entry_points_write_csv_and_structures(tmp_path):
     assert (tmp_path / "o.pdb").exists() and 0 <= best["index"] < 3 and best["lig_pos"].shape == (L, 3, 3)
 
 
-STAT = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "stat_1QA9_dips_s20.pt")
+GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+# (golden file, checkpoint in oracle/_ref, sampler keyword arguments)
+STAT_CASES = {
+    "base_dips_20": ("stat_1QA9_dips_s20.pt", "dips_model_0.pt", {}),
+    # BASELINE config #2: src/inference.py's sampler (all-atom centroid, clash force), weights/pinder_0.ckpt, 40 steps
+    "config2_pinder_clash_40": ("stat_1QA9_pinder_s40_clash.pt", "pinder_0.pt", {"use_clash_force": True, "centre_mode": 1}),
+}
 
 
-@pytest.mark.skipif(not (__import__("os").path.exists(STAT) and __import__("os").path.exists(__import__("os").path.join(REAL, "dips_model_0.pt"))),
-                    reason="statistical golden or oracle/_ref (real checkpoint + complex) not present")
-def test_free_running_sampler_matches_reference_distribution():
-    """T5: 256 free-running trajectories of the batched Philox sampler (tensor-core path) against 96
-    trajectories of the UNMODIFIED reference sampler (tests/golden/make_stat_golden.py: real dips checkpoint, 1QA9,
-    20 steps).  Two-sample Kolmogorov-Smirnov on final energy, ligand RMSD, |tr_update| and |rot_update|: p > 1e-3 each
-    (a wrong schedule, noise scale, centre convention or score sign shifts these distributions by many sigma)."""
+@pytest.mark.parametrize("case", list(STAT_CASES))
+def test_free_running_sampler_matches_reference_distribution(case):
+    """T5: 256 free-running trajectories of the batched Philox sampler (tensor-core path) against 64-96
+    trajectories of the UNMODIFIED reference sampler on 1QA9 with a real checkpoint (tests/golden/make_stat_golden.py).
+    Two-sample Kolmogorov-Smirnov on final energy, ligand RMSD, |tr_update| and |rot_update|: p > 1e-3 each
+    (a wrong schedule, noise scale, centre convention, clash force or score sign shifts these distributions by many sigma)."""
     import os
     from scipy.stats import ks_2samp
     from dfmdock_b200 import Score_Model
     from dfmdock_b200.features import batch_from_record
-    g = torch.load(STAT, weights_only=False)
-    ck = torch.load(os.path.join(REAL, "dips_model_0.pt"), weights_only=False)
+    gold, ckpt, kw = STAT_CASES[case]
+    if not (os.path.exists(os.path.join(GOLD, gold)) and os.path.exists(os.path.join(REAL, ckpt))):
+        pytest.skip("statistical golden or oracle/_ref (real checkpoint + complex) not present")
+    g = torch.load(os.path.join(GOLD, gold), weights_only=False)
+    ck = torch.load(os.path.join(REAL, ckpt), weights_only=False)
     model = Score_Model(ck["state_dict"], ck["hparams"], precision="fp16").to("cuda")
     batch = batch_from_record(torch.load(os.path.join(REAL, "db5_1QA9.pt"), weights_only=False), pos_width=model.pos_width)
     model.set_complex(batch)
-    res = model.sample(batch["lig_pos"], 256, num_steps=int(g["num_steps"]), seed=1234)
+    res = model.sample(batch["lig_pos"], 256, num_steps=int(g["num_steps"]), seed=1234, **kw)
     native = batch["lig_pos"][:, 1].double()
     mine = {
         "energy": res["energy"].cpu().double(),
@@ -449,6 +457,6 @@ def test_free_running_sampler_matches_reference_distribution():
         assert torch.isfinite(v).all(), k
         st = ks_2samp(v.numpy(), g[k].double().numpy())
         report[k] = (float(st.statistic), float(st.pvalue), float(v.mean()), float(g[k].double().mean()))
-    print("KS (statistic, p, mean cuda, mean reference):", report)
+    print("KS %s (statistic, p, mean cuda, mean reference):" % case, report)
     for k, (stat, pval, _, _) in report.items():
         assert pval > 1e-3, (k, report)
