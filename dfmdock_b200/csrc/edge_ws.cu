@@ -43,12 +43,22 @@ constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 102
 
 constexpr int NPROD = 16;                // producer warps
 constexpr int NEPI = 8;                  // epilogue warps
-// 28 warps: 8 producers, 16 epilogue, 1 MMA issuer + 3 idle warps that only complete its warpgroup (setmaxnreg is a
+// 28 warps: 16 producers, 8 epilogue, 1 MMA issuer + 2 loaders + 1 idle warp that completes the warpgroup (setmaxnreg is a
 // warpgroup-wide operation: a lone 17th warp never finishes it and the epilogue's .inc then blocks forever).
 constexpr int NT = (NPROD + NEPI + 4) * 32;   // 896 -> 72 registers/thread at launch, pool 28*32*72 = 64512
-constexpr int PROD_REGS = 64;            // setmaxnreg: 16*32*64 + 8*32*104 + 4*32*40 = 64512 <= 64512
-constexpr int EPI_REGS = 104;
-constexpr int MMA_REGS = 40;
+#ifndef EWS_PROD_REGS
+#define EWS_PROD_REGS 72
+#endif
+#ifndef EWS_EPI_REGS
+#define EWS_EPI_REGS 88
+#endif
+#ifndef EWS_MMA_REGS
+#define EWS_MMA_REGS 40
+#endif
+constexpr int PROD_REGS = EWS_PROD_REGS;  // setmaxnreg: 16*32*72 + 8*32*88 + 4*32*40 = 64512 = the launch pool (28 warps x 32 x 72)
+constexpr int EPI_REGS = EWS_EPI_REGS;
+constexpr int MMA_REGS = EWS_MMA_REGS;
+static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEPI + 4) * 72, "register pool exceeded");
 #ifndef EWS_EXP
 #define EWS_EXP 0      // diagnostic experiments (wrong results): 1 = B rows from row 0, 2 = table rows from row 0, 4 = no tanh
 #endif
