@@ -38,7 +38,12 @@ constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [16 producer warps][
 constexpr uint32_t OFF_JRING = OFF_META + 16 * 2 * 8 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
 constexpr uint32_t OFF_VEC32 = OFF_JRING + 2 * 2 * 128 * 4; // b2/2 [256] float, wa [256] float (fp32 epilogue)
 constexpr uint32_t OFF_BAR = OFF_VEC32 + 2048;            // 16 mbarriers + tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 160;
+// b2 folded into the accumulator by one extra K = 16 MMA per tile: A = [128 x 16] of 1/16, B = [256 x 16] with row n = b2[n]/2
+// (both K-major, no swizzle: 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row groups 256 B apart)
+constexpr uint32_t OFF_BIASA = (OFF_BAR + 160 + 127) & ~127u;
+constexpr uint32_t OFF_BIASB = OFF_BIASA + 128 * 32;
+constexpr uint32_t SMEM_BYTES = OFF_BIASB + 256 * 32;
+static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 1024-byte alignment
 
 constexpr int NPROD = 16;                // producer warps
@@ -74,9 +79,16 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_PIN_ADDR
 #define EWS_PIN_ADDR 0
 #endif
+#ifndef EWS_BIAS_MMA
+#define EWS_BIAS_MMA 1    // b2 enters the accumulator through the tensor core instead of 64 HADD2 per epilogue thread and tile
+#endif
+#ifndef EWS_BIAS_DESC
+#define EWS_BIAS_DESC 0   // 0: LBO = 128 B (K chunk), SBO = 256 B (8-row group); 1: swapped (descriptor bring-up switch)
+#endif
 #ifndef EWS_EPI_V3
 #define EWS_EPI_V3 1      // epilogue on tcgen05.ld.16x256b fragments: a thread holds 4 rows x 16 column pairs, so the gated
 #endif                    // segment sum is mostly in-thread FMAs (14 shuffle steps instead of 63)
+static_assert(!EWS_BIAS_MMA || EWS_EPI_V3, "the bias MMA belongs to the fragment epilogue (the older epilogues add b2 themselves)");
 #ifndef EWS_EPI_PIPE
 #define EWS_EPI_PIPE 1    // epilogue: 8-column tcgen05.ld double buffered (next chunk in flight while this one is computed)
 #endif
@@ -94,6 +106,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   // K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // K-major, no swizzle (layout type 0): start>>4 | LBO>>4 at bit 16 | SBO>>4 at bit 32 | version 1
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -315,6 +332,19 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 #endif
     }
   }
+#if EWS_BIAS_MMA
+  {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + OFF_BIASA);
+    for (int i = tid; i < 128 * 32 / 4; i += NT) ones[i] = 0x2C002C00u;             // half2(1/16, 1/16)
+    // row n, K chunk c (8 halfs): byte offset (n >> 3) * 256 + c * 128 + (n & 7) * 16
+    for (int i = tid; i < 256 * 2; i += NT) {
+      const int n = i >> 1, c = i & 1;
+      const __half2 b = __half2half2(__float2half_rn(0.5f * p.b2[n]));
+      const uint32_t bits = *reinterpret_cast<const uint32_t*>(&b);
+      *reinterpret_cast<uint4*>(smem + OFF_BIASB + (n >> 3) * 256 + c * 128 + (n & 7) * 16) = make_uint4(bits, bits, bits, bits);
+    }
+  }
+#endif
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
@@ -453,12 +483,20 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       if (lane == 0) {
         const uint64_t dW = make_desc(sbase + OFF_W);
         const uint64_t dS = make_desc(sbase + OFF_S);
+#if EWS_BIAS_MMA
+        const uint64_t dOnes = make_desc_noswz(sbase + OFF_BIASA, EWS_BIAS_DESC ? 256u : 128u, EWS_BIAS_DESC ? 128u : 256u);
+        const uint64_t dBias = make_desc_noswz(sbase + OFF_BIASB, EWS_BIAS_DESC ? 256u : 128u, EWS_BIAS_DESC ? 128u : 256u);
+#endif
         unsigned long long tw0 = 0, tw1 = 0;
         int it = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++it) {
           const int buf = it & 1;
           if (it >= 2) TWAIT(tw1, mbar_wait<0>(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1)));   // epilogue drained this buffer
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+#if EWS_BIAS_MMA
+          tc_fence_after();
+          mma_f16(d_tmem, dOnes, dBias, 0u);      // D = 1 * (b2/2)^T: needs no producer, so it goes first
+#endif
 #pragma unroll 1
           for (int kb = 0; kb < 4; ++kb) {
             TWAIT(tw0, mbar_wait<0>(bar_full + 8 * kb, (uint32_t)(it & 1)));
@@ -467,7 +505,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t da = dS + (uint64_t)((kb * S_KBLK + k4 * 32) >> 4);
               const uint64_t db = dW + (uint64_t)((kb * W_KBLK + k4 * 32) >> 4);
-              mma_f16(d_tmem, da, db, (kb | k4) ? 1u : 0u);
+              mma_f16(d_tmem, da, db, (EWS_BIAS_MMA || (kb | k4)) ? 1u : 0u);
             }
             mma_commit(bar_empty + 8 * kb);
           }
@@ -586,15 +624,22 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
           tmem_ld_wait8(cur);
           if (n + 1 < 16) tmem_ld16x256_x2_issue(frag_addr(n + 1), nxt);
           if ((n & 3) == 0) {
-            bb = lds128(vx_s + (uint32_t)g * 16u);
+            if (!EWS_BIAS_MMA) bb = lds128(vx_s + (uint32_t)g * 16u);
             ww = lds128(vx_s + 640u + (uint32_t)g * 16u);
           }
-          const uint32_t b0 = half ? bb.z : bb.x, b1 = half ? bb.w : bb.y;
           const uint32_t w0 = half ? ww.z : ww.x, w1 = half ? ww.w : ww.y;
+#if EWS_BIAS_MMA
+          const uint32_t x00 = h2silu(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])));
+          const uint32_t x10 = h2silu(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])));
+          const uint32_t x01 = h2silu(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])));
+          const uint32_t x11 = h2silu(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])));
+#else
+          const uint32_t b0 = half ? bb.z : bb.x, b1 = half ? bb.w : bb.y;
           const uint32_t x00 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), b0));
           const uint32_t x10 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), b0));
           const uint32_t x01 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), b1));
           const uint32_t x11 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), b1));
+#endif
           m[(2 * hh) * 16 + 2 * jj] = x00; m[(2 * hh) * 16 + 2 * jj + 1] = x01;
           m[(2 * hh + 1) * 16 + 2 * jj] = x10; m[(2 * hh + 1) * 16 + 2 * jj + 1] = x11;
           dA[hh] = h2fma(x00, w0, dA[hh]); dA[hh] = h2fma(x01, w1, dA[hh]);
