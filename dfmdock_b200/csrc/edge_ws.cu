@@ -77,7 +77,7 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #define EWS_ROW_INTERLEAVE 0   // (measured slower: 1.29 vs 1.21 ms) producer warp w builds slots {w&7, (w&7)+8, ...} of its residue instead of 8 consecutive slots:
 #endif                         // every warp gets the same mix of kNN slots (two table gathers) and far slots (one)
 #ifndef EWS_PIN_ADDR
-#define EWS_PIN_ADDR 0
+#define EWS_PIN_ADDR 1
 #endif
 #ifndef EWS_BIAS_MMA
 #define EWS_BIAS_MMA 1    // b2 enters the accumulator through the tensor core instead of 64 HADD2 per epilogue thread and tile
@@ -390,28 +390,35 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const int r = prow(rsub + 4 * i);
       soff[i] = sbase + OFF_S + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
     }
+    uint32_t pbar = sbase + OFF_BAR;          // this role's copy of the barrier block address (full at +0, bfull at +96)
 #if EWS_PIN_ADDR
-    // opaque to the compiler: keeps these four addresses in registers instead of re-deriving them from %tid and the
+    // opaque to the compiler: keeps these addresses in registers instead of re-deriving them from %tid and the
     // shared window base in every K block (ptxas otherwise rematerialises ~25 instructions per K block)
-    asm volatile("" : "+r"(soff[0]), "+r"(soff[1]), "+r"(mring_s), "+r"(vwr_s));
+    asm volatile("" : "+r"(soff[0]), "+r"(soff[1]), "+r"(mring_s), "+r"(vwr_s), "+r"(pbar));
+#endif
+    // per-lane views: this lane's rows of a metadata slot start at + rsub * 16; table / A pointers already at column c8 * 8
+    uint32_t mlane = (uint32_t)rsub * 16u;
+    const __half* tdrp_l = p.Tdrp + c8 * 8;
+    const __half* totp_l = p.Totp + c8 * 8;
+#if EWS_PIN_ADDR
+    asm volatile("" : "+r"(mlane), "+l"(tdrp_l), "+l"(totp_l));
 #endif
     auto issue = [&](GBuf& g, uint32_t mslot, size_t aoff, int kb) {
-      const int colh = kb * 64 + c8 * 8;
       g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        uint4 mt = lds128(mslot + (uint32_t)(4 * i + rsub) * 16u);
+        uint4 mt = lds128(mslot + mlane + (uint32_t)(4 * i) * 16u);
         if (EWS_EXP & 2) { mt.y = 0; mt.z = ((int)mt.z >= 0) ? 0u : mt.z; }
-        g.td[i] = __ldg(reinterpret_cast<const uint4*>(p.Tdrp + (size_t)mt.y * H + colh));
+        g.td[i] = __ldg(reinterpret_cast<const uint4*>(tdrp_l + (size_t)mt.y * H + kb * 64));
         g.to[i] = make_uint4(0, 0, 0, 0);
-        if ((int)mt.z >= 0) g.to[i] = __ldg(reinterpret_cast<const uint4*>(p.Totp + (size_t)mt.z * H + colh));
+        if ((int)mt.z >= 0) g.to[i] = __ldg(reinterpret_cast<const uint4*>(totp_l + (size_t)mt.z * H + kb * 64));
       }
     };
     auto compute = [&](const GBuf& g, uint32_t mslot, int kb) {
       const uint4 wr = lds128(vwr_s + (uint32_t)kb * 128u);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t rad = lds32(mslot + (uint32_t)(4 * i + rsub) * 16u + 12u);
+        const uint32_t rad = lds32(mslot + mlane + (uint32_t)(4 * i) * 16u + 12u);
         const uint32_t sa = soff[i] + (uint32_t)kb * S_KBLK;
         const uint4 hb = lds128(sa);
         uint4 o;
@@ -454,26 +461,26 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const uint32_t par = (uint32_t)(it & 1);
       // kb 0 (buffer 0); prefetch kb 1
       issue(g1, mcur, ao, 1);
-      TWAIT(tw0, mbar_wait<100>(bar_bfull + 0, par));
+      TWAIT(tw0, mbar_wait<100>(pbar + 96u, par));
       compute(g0, mcur, 0);
-      fence_async_smem(); mbar_arrive(bar_full + 0);
+      fence_async_smem(); mbar_arrive(pbar + 0u);
       // kb 1 (buffer 1); prefetch kb 2
       issue(g0, mcur, ao, 2);
-      TWAIT(tw0, mbar_wait<100>(bar_bfull + 8, par));
+      TWAIT(tw0, mbar_wait<100>(pbar + 104u, par));
       compute(g1, mcur, 1);
-      fence_async_smem(); mbar_arrive(bar_full + 8);
+      fence_async_smem(); mbar_arrive(pbar + 8u);
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
-      TWAIT(tw0, mbar_wait<100>(bar_bfull + 16, par));
+      TWAIT(tw0, mbar_wait<100>(pbar + 112u, par));
       compute(g0, mcur, 2);
-      fence_async_smem(); mbar_arrive(bar_full + 16);
+      fence_async_smem(); mbar_arrive(pbar + 16u);
       // kb 3 (buffer 1); stage the next tile's metadata (its load has had three K blocks to land), prefetch its kb 0
       if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
       __syncwarp();
       if (has_next) issue(g0, mnext, aon, 0);
-      TWAIT(tw0, mbar_wait<100>(bar_bfull + 24, par));
+      TWAIT(tw0, mbar_wait<100>(pbar + 120u, par));
       compute(g1, mcur, 3);
-      fence_async_smem(); mbar_arrive(bar_full + 24);
+      fence_async_smem(); mbar_arrive(pbar + 24u);
     }
     if (EWS_TIMING && warp == 0 && lane == 0) { atomicAdd(p.timing + 0, tw0); atomicAdd(p.timing + 1, (unsigned long long)(clock64() - tstart)); }
   } else if (warp >= NPROD + NEPI) {
