@@ -85,6 +85,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_BIAS_DESC
 #define EWS_BIAS_DESC 0   // 0: LBO = 128 B (K chunk), SBO = 256 B (8-row group); 1: swapped (descriptor bring-up switch)
 #endif
+#ifndef EWS_FOLD
+#define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
+#endif
 #ifndef EWS_EPI_V3
 #define EWS_EPI_V3 1      // epilogue on tcgen05.ld.16x256b fragments: a thread holds 4 rows x 16 column pairs, so the gated
 #endif                    // segment sum is mostly in-thread FMAs (14 shuffle steps instead of 63)
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
           m[(2 * hh + 1) * 16 + 2 * jj] = x10; m[(2 * hh + 1) * 16 + 2 * jj + 1] = x11;
           dA[hh] = h2fma(x00, w0, dA[hh]); dA[hh] = h2fma(x01, w1, dA[hh]);
           dB[hh] = h2fma(x10, w0, dB[hh]); dB[hh] = h2fma(x11, w1, dB[hh]);
-          if ((g & 1) && half) {    // 8 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
+          if ((((g & (EWS_FOLD / 4 - 1)) == EWS_FOLD / 4 - 1) || g == 3) && half) {   // EWS_FOLD products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
             const float2 fa = h2f2(dA[hh]), fb = h2f2(dB[hh]);
             dot[2 * hh] += fa.x + fa.y; dot[2 * hh + 1] += fb.x + fb.y;
             dA[hh] = dB[hh] = 0;
