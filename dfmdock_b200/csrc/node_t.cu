@@ -19,10 +19,13 @@ namespace ntt {
 constexpr uint32_t W_BYTES = 256 * 256 * 2;          // 128 KB in every mode
 constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_S = W_BYTES;                  // operand ring, 64 KB
-constexpr uint32_t RING_BYTES = 65536;
+#ifndef NTT_RING_KB
+#define NTT_RING_KB 64
+#endif
+constexpr uint32_t RING_BYTES = NTT_RING_KB * 1024;
 constexpr uint32_t OFF_VEC = OFF_S + RING_BYTES;     // 256 floats bias
-constexpr uint32_t OFF_BAR = OFF_VEC + 1024;         // full[8], empty[8], accf[4], acce[4], tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
+constexpr uint32_t OFF_BAR = OFF_VEC + 1024;         // full[16], empty[16], accf[4], acce[4], tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 384;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;
 constexpr int NWORK = 16;
 constexpr int NT = (NWORK + 3) * 32;                 // 608
@@ -132,9 +135,10 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* vbias = reinterpret_cast<float*>(smem + OFF_VEC);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 240);
-  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 64;
-  const uint32_t bar_accf = sbase + OFF_BAR + 128, bar_acce = sbase + OFF_BAR + 160;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 336);
+  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 128;
+  const uint32_t bar_accf = sbase + OFF_BAR + 256, bar_acce = sbase + OFF_BAR + 288;
+  static_assert(NSLOT <= 16, "barrier block holds 16 ring slots");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int half_grid = (int)gridDim.x >> 1;
