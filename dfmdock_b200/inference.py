@@ -374,3 +374,5 @@ if __name__ == "__main__":
     _args = build_parser().parse_args()
     set_seed(_args.seed)
     main(_args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
