@@ -331,6 +331,7 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     if ((rc = launch_node_ab(ctx, l, M, ws.h16, Ah, Bm, s))) return rc;
     EdgeArgs ea{};
     ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
+    ea.lig_only = last && !want_energy;   // the receptor rows' layer-5 messages only feed the node update the energy head needs
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
     ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf; ea.coord_img = w.img_Wc1s;
     const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();

@@ -184,6 +184,7 @@ struct EdgeArgs {
   int B, N, R, K;
   int layer;
   bool last;            // coordinate update for ligand rows
+  bool lig_only;        // last layer, no energy head wanted: only the tiles that hold a ligand residue are needed
   const int32_t* nbr;
   const uint32_t* feat;
   const float* radial;

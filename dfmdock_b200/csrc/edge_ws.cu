@@ -85,6 +85,19 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_BIAS_DESC
 #define EWS_BIAS_DESC 0   // 0: LBO = 128 B (K chunk), SBO = 256 B (8-row group); 1: swapped (descriptor bring-up switch)
 #endif
+// back-off (ns) between mbarrier polls per role: producers, MMA issuer, B_j loaders, epilogue
+#ifndef EWS_SLEEP_P
+#define EWS_SLEEP_P 100
+#endif
+#ifndef EWS_SLEEP_M
+#define EWS_SLEEP_M 0
+#endif
+#ifndef EWS_SLEEP_L
+#define EWS_SLEEP_L 100
+#endif
+#ifndef EWS_SLEEP_E
+#define EWS_SLEEP_E 200
+#endif
 #ifndef EWS_FOLD
 #define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
 #endif
@@ -238,6 +251,8 @@ struct Params {
   int total_nodes;          // B * N
   int N, R, K;
   int last;                 // spill gated messages of ligand residues (coordinate head input)
+  int lig_only;             // last layer without the energy head: only tiles that hold a ligand residue are processed (the
+  int tpt;                  // receptor rows' segment sums would feed a node update that is never run); tpt = such tiles per trajectory
   const __half* Wimg;       // (W2 / 2) fp16 SW128 image
   const int4* emeta;        // [B*N, 64] {global row of j, Tdrp row, Totp row or -1, radial bits}
   const __half* Ahi;        // [B*N, 256] fp16((W1s h_i + b1)/2)
@@ -367,6 +382,14 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   // not hot lines shared by all SMs (strided assignment had every SM hammer the same 300 rows at the same time)
   const int t_begin = (int)blockIdx.x * p.chunk;
   const int t_end = min(p.ntiles, t_begin + p.chunk);
+  // logical tile index -> tile of the [B*N/2] node-pair grid.  Ligand-only launches walk, per trajectory, the tiles
+  // (b N + R) / 2 .. (b N + N - 1) / 2; when that count is one short of tpt (odd N) the last tile is simply done twice.
+  auto phys = [&](int lt) -> int {
+    if (!p.lig_only) return lt;
+    const int b = lt / p.tpt, r = lt - b * p.tpt;
+    const int base = b * p.N;
+    return min(((base + p.R) >> 1) + r, (base + p.N - 1) >> 1);
+  };
 
   if (warp < NPROD) {
     // =================================== PRODUCERS ===================================================
@@ -432,15 +455,15 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         sts128(sa, o);
       }
     };
-    auto load_meta = [&](int tile) -> int4 {     // lanes 0..7: edge metadata of row warp*8 + lane of `tile`
+    auto load_meta = [&](int lt) -> int4 {       // lanes 0..7: edge metadata of row warp*8 + lane of logical tile `lt`
       int4 mt = pad_meta;
       const int r = prow(lane & 7);
-      const int node = tile * 2 + (r >> 6);
-      if (tile < t_end && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
+      const int node = phys(lt) * 2 + (r >> 6);
+      if (lt < t_end && node < p.total_nodes) mt = __ldg(p.emeta + (size_t)node * SLOTS + (r & 63));
       return mt;
     };
-    auto a_node = [&](int tile) -> size_t {
-      int node = tile * 2 + (warp >> 3);
+    auto a_node = [&](int lt) -> size_t {
+      int node = phys(lt) * 2 + (warp >> 3);
       if (node >= p.total_nodes) node = p.total_nodes - 1;   // odd tail: those rows are masked in the epilogue
       return (size_t)node * H + c8 * 8;
     };
@@ -464,24 +487,24 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const uint32_t par = (uint32_t)(it & 1);
       // kb 0 (buffer 0); prefetch kb 1
       issue(g1, mcur, ao, 1);
-      TWAIT(tw0, mbar_wait<100>(pbar + 96u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 96u, par));
       compute(g0, mcur, 0);
       fence_async_smem(); mbar_arrive(pbar + 0u);
       // kb 1 (buffer 1); prefetch kb 2
       issue(g0, mcur, ao, 2);
-      TWAIT(tw0, mbar_wait<100>(pbar + 104u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 104u, par));
       compute(g1, mcur, 1);
       fence_async_smem(); mbar_arrive(pbar + 8u);
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
-      TWAIT(tw0, mbar_wait<100>(pbar + 112u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 112u, par));
       compute(g0, mcur, 2);
       fence_async_smem(); mbar_arrive(pbar + 16u);
       // kb 3 (buffer 1); stage the next tile's metadata (its load has had three K blocks to land), prefetch its kb 0
       if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
       __syncwarp();
       if (has_next) issue(g0, mnext, aon, 0);
-      TWAIT(tw0, mbar_wait<100>(pbar + 120u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 120u, par));
       compute(g1, mcur, 3);
       fence_async_smem(); mbar_arrive(pbar + 24u);
     }
@@ -501,7 +524,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         int it = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++it) {
           const int buf = it & 1;
-          if (it >= 2) TWAIT(tw1, mbar_wait<0>(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1)));   // epilogue drained this buffer
+          if (it >= 2) TWAIT(tw1, mbar_wait<EWS_SLEEP_M>(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1)));   // epilogue drained this buffer
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
 #if EWS_BIAS_MMA
           tc_fence_after();
@@ -509,7 +532,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 #endif
 #pragma unroll 1
           for (int kb = 0; kb < 4; ++kb) {
-            TWAIT(tw0, mbar_wait<0>(bar_full + 8 * kb, (uint32_t)(it & 1)));
+            TWAIT(tw0, mbar_wait<EWS_SLEEP_M>(bar_full + 8 * kb, (uint32_t)(it & 1)));
             tc_fence_after();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -531,18 +554,18 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       // j ring: [2 slots][4 row residues][32] -> the 32 rows (rsub + 4 i) of one lane are contiguous (8 x LDS.128)
       const uint32_t jring_s = sbase + OFF_JRING + (uint32_t)lw * 1024u;
       const int c8 = lane & 7, rsub = lane >> 3;
-      auto load_j = [&](int tile, int i) -> int {        // global row of the neighbour of tile row lane + 32 i
+      auto load_j = [&](int ptile, bool inrange, int i) -> int {   // global row of the neighbour of tile row lane + 32 i
         const int r = lane + 32 * i;
-        const int node = tile * 2 + (r >> 6);
+        const int node = ptile * 2 + (r >> 6);
         int j = 0;
-        if (tile < t_end && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
+        if (inrange && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
         return j;
       };
       // row r = lane + 32 i sits at ring index (r & 3) * 32 + (r >> 2)
       const uint32_t jput = (uint32_t)((lane & 3) * 32 + (lane >> 2)) * 4u;
       if (t_begin < t_end) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(t_begin, i));
+        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(phys(t_begin), true, i));
       }
       __syncwarp();
       // destination of this lane's chunk in row rsub + 4 i: (rsub + 4 i) * 128 + ((c8 ^ ((rsub + 4 i) & 7)) << 4);
@@ -555,12 +578,14 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u + (uint32_t)rsub * 128u;
         int jn[4];
+        const bool nin = tile + 1 < t_end;
+        const int nptile = nin ? phys(tile + 1) : 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) jn[i] = load_j(tile + 1, i);
+        for (int i = 0; i < 4; ++i) jn[i] = load_j(nptile, nin, i);
 #pragma unroll 1
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = lw + 2 * kk;
-          if (it > 0) TWAIT(tw0, mbar_wait<100>(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1)));
+          if (it > 0) TWAIT(tw0, mbar_wait<EWS_SLEEP_L>(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1)));
           const char* src0 = srcb + kb * 128;
           const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)rsub * 128u;
 #pragma unroll
@@ -609,8 +634,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     (void)erow; (void)vec_s; (void)vec32_s; (void)part_s;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int buf = it & 1;
-      const int node = tile * 2 + hn;
-      TWAIT(tw0, mbar_wait<200>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
+      const int node = phys(tile) * 2 + hn;
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_E>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
       uint32_t m[64];
@@ -708,6 +733,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
             }
           }
         }
+        if (p.lig_only) continue;     // no node update follows this launch: the segment sum would never be read
 #pragma unroll
         for (int j = 0; j < 16; ++j) sacc[j] = h2add(h2add(m[j], m[16 + j]), h2add(m[32 + j], m[48 + j]));
       } else {
@@ -733,9 +759,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 #else
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int buf = it & 1;
-      const int node = tile * 2 + hn, k = erow & 63;
+      const int node = phys(tile) * 2 + hn, k = erow & 63;
       const bool valid = node < p.total_nodes && k < p.K;
-      TWAIT(tw0, mbar_wait<200>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_E>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
       uint32_t m[64];
@@ -875,6 +901,13 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   p.ntiles = (p.total_nodes + 1) / 2;
   p.N = a.N; p.R = a.R; p.K = a.K;
   p.last = a.last ? 1 : 0;
+  p.lig_only = (a.last && a.lig_only && a.N > a.R && a.R > 1) ? 1 : 0;
+  if (p.lig_only) {
+    const int L2a = ((a.N - 1) >> 1) - (a.R >> 1) + 1;                  // b N even
+    const int L2b = (a.N >> 1) - ((a.R + 1) >> 1) + 1;                  // b N odd (only when N is odd)
+    p.tpt = (a.N & 1) ? (L2a > L2b ? L2a : L2b) : L2a;
+    p.ntiles = a.B * p.tpt;
+  }
   p.Wimg = w.img_W2h;
   p.emeta = emeta;
   p.Ahi = Ahi; p.Alo = nullptr;
