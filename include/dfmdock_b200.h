@@ -43,7 +43,9 @@ enum {
 
 /* dfm_score_forward / dfm_sample flags */
 enum {
-  DFM_WANT_ENERGY = 1u << 0,   /* run the pair-energy head + clash count (final forward only in the sampler) */
+  DFM_WANT_ENERGY = 1u << 0,   /* run the pair-energy head + clash count (final forward only in the sampler); without it the
+                                  last layer only processes the ligand residues' edges: the receptor rows' layer-5 messages
+                                  feed a node update nothing but the energy head consumes */
   DFM_PRECISION_FP32 = 1u << 1,/* fp32 FFMA kernels (parity mode); default = fp16-operand tcgen05 kernels, fp32 accumulate */
   DFM_CLASH_FORCE = 1u << 2,   /* inference.py:358-361 soft-clash translation after every step */
   DFM_NOISE_ANNEAL = 1u << 3,  /* noise_scale = t (inference_base.py:428-430) */
