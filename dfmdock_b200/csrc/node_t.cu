@@ -12,6 +12,8 @@
 // 1 MMA issuer.  Tiles are 64 rows (AB, H: two 128-feature halves -> 2 x 64 accumulator columns) or 128 rows (Z: one
 // 128-feature half of the output per grid half, K = 512); the operand ring holds 64 KB = 8 or 4 K blocks, the
 // accumulator (128 TMEM columns per tile) is quadruple buffered.
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace ntt {
@@ -99,7 +101,20 @@ __device__ __forceinline__ float silu_tanh(float x) {
 
 enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2 };
 
+#ifndef NTT_BULK_W
+#define NTT_BULK_W 1   // weight image by cp.async.bulk (TMA 1-D) overlapped with the set-up instead of 14 rounds of LDG + STS
+#endif
+#ifndef NTT_TIMING
+#define NTT_TIMING 0   // 1: per-role wait cycles (diagnostic builds), printed every 16 launches of a mode
+#endif
+#if NTT_TIMING
+#define NTWAIT(acc, call) do { const long long _t0 = clock64(); call; acc += (unsigned long long)(clock64() - _t0); } while (0)
+#else
+#define NTWAIT(acc, call) do { call; } while (0)
+#endif
+
 struct Params {
+  unsigned long long* timing;   // NTT_TIMING: [8] {prologue, mma wait full, mma wait acce, mma total, loader wait empty, loader total, worker wait accf, worker total}
   int M, ntiles, N;
   // MODE_AB: X = h16; CTAs [0, grid/2) use W0/bias0/out0, the rest W1/(no bias)/out1; out = fp16(0.5 * (acc + bias))
   // MODE_Z : K blocks 0-3 from X = h16, 4-7 from X2 = agg16; CTAs [0, grid/2) use W0 (output features 0-127), the
@@ -138,8 +153,10 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 336);
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 128;
   const uint32_t bar_accf = sbase + OFF_BAR + 256, bar_acce = sbase + OFF_BAR + 288;
+  const uint32_t bar_w = sbase + OFF_BAR + 352;
   static_assert(NSLOT <= 16, "barrier block holds 16 ring slots");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_kernel = clock64();
 
   const int half_grid = (int)gridDim.x >> 1;
   const int side = (SPLIT && (int)blockIdx.x >= half_grid) ? 1 : 0;
@@ -147,9 +164,11 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   const int ncta = SPLIT ? half_grid : (int)gridDim.x;
 
   {
+#if !NTT_BULK_W
     const uint4* src = reinterpret_cast<const uint4*>(side ? p.W1 : p.W0);
     uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
     for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
+#endif
     if (tid < 256) {
       float b = p.bias0 ? p.bias0[tid] : 0.f;
       if (MODE == MODE_AB && side) b = 0.f;
@@ -159,7 +178,20 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
+#if NTT_BULK_W
+    mbar_init(bar_w, 1);
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#if NTT_BULK_W
+    // the 128 KB weight image arrives by four bulk copies (async proxy) while the CTA finishes its set-up and the loaders
+    // already fetch the first tiles; only the MMA issuer waits for it
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(W_BYTES) : "memory");
+    const char* wsrc = reinterpret_cast<const char*>(side ? p.W1 : p.W0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sbase + OFF_W + (uint32_t)i * (W_BYTES / 4)), "l"(wsrc + (size_t)i * (W_BYTES / 4)), "r"(W_BYTES / 4), "r"(bar_w) : "memory");
+#endif
   }
   if (warp == NWORK + 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
@@ -170,6 +202,9 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_start = clock64();
+  if (NTT_TIMING && tid == 0) atomicAdd(p.timing + 0, (unsigned long long)(t_start - t_kernel));
+  unsigned long long tw0 = 0, tw1 = 0;
 
   if (warp == NWORK + 2) {
     // =================================== MMA ISSUER ===================================================
@@ -178,15 +213,18 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
       const uint64_t dS = make_desc(sbase + OFF_S);
       int it = 0;
       uint32_t c = 0;                                        // running K-block count -> ring slot / phase
+#if NTT_BULK_W
+      mbar_wait(bar_w, 0u);                                  // weight image landed
+#endif
       for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
         const int buf = it % NACC;
         const int use = it / NACC;
-        if (use >= 1) mbar_wait(bar_acce + 8 * buf, (uint32_t)((use - 1) & 1));
+        if (use >= 1) NTWAIT(tw1, mbar_wait(bar_acce + 8 * buf, (uint32_t)((use - 1) & 1)));
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb, ++c) {
           const uint32_t slot = c % NSLOT;
-          mbar_wait(bar_full + 8 * slot, (c / NSLOT) & 1u);
+          NTWAIT(tw0, mbar_wait(bar_full + 8 * slot, (c / NSLOT) & 1u));
           tc_fence_after();
 #pragma unroll
           for (int hf = 0; hf < NHALF; ++hf) {
@@ -202,6 +240,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
         }
         mma_commit(bar_accf + 8 * buf);
       }
+      if (NTT_TIMING) { atomicAdd(p.timing + 1, tw0); atomicAdd(p.timing + 2, tw1); atomicAdd(p.timing + 3, (unsigned long long)(clock64() - t_start)); }
     }
     __syncwarp();
   } else if (warp >= NWORK) {
@@ -216,7 +255,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
         for (int kb = 0; kb < KB; ++kb, ++c) {
           if ((kb & 1) != lw) continue;
           const uint32_t slot = c % NSLOT;
-          if (c >= (uint32_t)NSLOT) mbar_wait(bar_empty + 8 * slot, ((c / NSLOT) - 1) & 1u);
+          if (c >= (uint32_t)NSLOT) NTWAIT(tw0, mbar_wait(bar_empty + 8 * slot, ((c / NSLOT) - 1) & 1u));
           const __half* X = (MODE == MODE_Z && kb >= 4) ? p.X2 : p.X;
           const int kcol = (kb & 3) * 64 + c8 * 8;
           const uint32_t dst0 = sbase + OFF_S + slot * SLOT_BYTES;
@@ -231,6 +270,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
         }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
+      if (NTT_TIMING && warp == NWORK && lane == 0) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, (unsigned long long)(clock64() - t_start)); }
     }
     __syncwarp();
   } else {
@@ -275,7 +315,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
 
     auto epilogue = [&](int tile, int it) {
       const int buf = it % NACC;
-      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it / NACC) & 1));
+      NTWAIT(tw0, mbar_wait(bar_accf + 8 * buf, (uint32_t)((it / NACC) & 1)));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + g * 32);
       float v[32];
@@ -332,6 +372,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     } else {
       for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) epilogue(tile, it);
     }
+    if (NTT_TIMING && tid == 0) { atomicAdd(p.timing + 6, tw0); atomicAdd(p.timing + 7, (unsigned long long)(clock64() - t_start)); }
   }
   tc_fence_before();
   __syncthreads();
@@ -348,6 +389,22 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
     attr = true;
   }
   if (grid <= 0) return 0;
+#if NTT_TIMING
+  static unsigned long long* tbuf = nullptr;
+  static int calls = 0;
+  if (!tbuf) { CUDA_TRY(cudaMalloc(&tbuf, 64)); CUDA_TRY(cudaMemset(tbuf, 0, 64)); }
+  Params q = p; q.timing = tbuf;
+  k_nodeT<MODE><<<grid, NT, SMEM_ALLOC, s>>>(q);
+  if (++calls % 16 == 0) {
+    unsigned long long hb[8];
+    cudaMemcpy(hb, tbuf, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ntt timing mode %d, sums over %d CTAs x 16 launches, kcycles] prologue %.0f | mma wait full %.0f acce %.0f of %.0f | loader wait empty %.0f of %.0f | worker0 wait accf %.0f of %.0f\n",
+            MODE, grid, hb[0] * 1e-3, hb[1] * 1e-3, hb[2] * 1e-3, hb[3] * 1e-3, hb[4] * 1e-3, hb[5] * 1e-3, hb[6] * 1e-3, hb[7] * 1e-3);
+    cudaMemset(tbuf, 0, 64);
+  }
+  LAUNCH_CHECK(ctx);
+  return 0;
+#endif
   k_nodeT<MODE><<<grid, NT, SMEM_ALLOC, s>>>(p);
   LAUNCH_CHECK(ctx);
   return 0;
