@@ -98,6 +98,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_SLEEP_E
 #define EWS_SLEEP_E 200
 #endif
+#ifndef EWS_BULK_W
+#define EWS_BULK_W 1      // weight image by cp.async.bulk (TMA 1-D), overlapped with the rest of the set-up and the first tile's build
+#endif
 #ifndef EWS_FOLD
 #define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
 #endif
@@ -322,13 +325,16 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   const uint32_t bar_empty = sbase + OFF_BAR + 32;      // [4]
   const uint32_t bar_accf = sbase + OFF_BAR + 64;       // [2]
   const uint32_t bar_acce = sbase + OFF_BAR + 80;       // [2]
+  const uint32_t bar_w = sbase + OFF_BAR + 128;         // weight image landed (bulk copy)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup ------------------------------------------------------------------------------
   {
+#if !EWS_BULK_W
     const uint4* src = reinterpret_cast<const uint4*>(p.Wimg);
     uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
     for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
+#endif
     if (tid < 256) {
       vb2[tid] = __float2half_rn(0.5f * p.b2[tid]);
       vwa[tid] = __float2half_rn(p.wa[tid]);
@@ -367,7 +373,20 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
     for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, 32);
+#if EWS_BULK_W
+    mbar_init(bar_w, 1);
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#if EWS_BULK_W
+    // the 128 KB weight image arrives by four bulk copies (async proxy) while the CTA finishes its set-up and the
+    // producers / loaders already work on the first tile; only the MMA issuer waits for it
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(W_BYTES) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sbase + OFF_W + (uint32_t)i * (W_BYTES / 4)), "l"(reinterpret_cast<const char*>(p.Wimg) + (size_t)i * (W_BYTES / 4)),
+                     "r"(W_BYTES / 4), "r"(bar_w) : "memory");
+#endif
   }
   if (warp == NPROD + NEPI) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
@@ -522,6 +541,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 #endif
         unsigned long long tw0 = 0, tw1 = 0;
         int it = 0;
+#if EWS_BULK_W
+        mbar_wait<20>(bar_w, 0u);
+#endif
         for (int tile = t_begin; tile < t_end; ++tile, ++it) {
           const int buf = it & 1;
           if (it >= 2) TWAIT(tw1, mbar_wait<EWS_SLEEP_M>(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1)));   // epilogue drained this buffer

@@ -147,11 +147,9 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
   const int cta = SPLIT ? ((int)blockIdx.x - side * half_grid) : (int)blockIdx.x;
   const int ncta = SPLIT ? half_grid : (int)gridDim.x;
 
-  // ---- setup: weight image (plain loads; visible to the tensor core after the fence below), vectors, barriers, TMEM
+  // ---- setup: weight image (four bulk copies, async proxy; only the MMA issuer waits for them), vectors, barriers, TMEM
+  const uint32_t bar_w = sbase + OFF_BAR + 96;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(side ? p.W1 : p.W0);
-    uint4* dst = reinterpret_cast<uint4*>(smem + OFF_W);
-    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
     if (tid < 256) {
       float b = p.bias0 ? p.bias0[tid] : 0.f;
       if (MODE == MODE_AB && side) b = 0.f;
@@ -162,7 +160,14 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
+    mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(W_BYTES) : "memory");
+    const char* wsrc = reinterpret_cast<const char*>(side ? p.W1 : p.W0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sbase + OFF_W + (uint32_t)i * (W_BYTES / 4)), "l"(wsrc + (size_t)i * (W_BYTES / 4)), "r"(W_BYTES / 4), "r"(bar_w) : "memory");
   }
   if (warp == NWORK + 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
       const uint64_t dS = make_desc(sbase + OFF_S);
       int it = 0;
       uint32_t c = 0;                                        // running K-block count -> ring slot / phase
+      mbar_wait(bar_w, 0u);                                  // weight image landed
       for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
         const int buf = it & 1;
         if (it >= 2) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));
