@@ -101,6 +101,9 @@ __device__ __forceinline__ float silu_tanh(float x) {
 
 enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2 };
 
+#ifndef NTT_AB_ROWS
+#define NTT_AB_ROWS 128   // rows per MODE_AB tile (64 or 128)
+#endif
 #ifndef NTT_BULK_W
 #define NTT_BULK_W 1   // weight image by cp.async.bulk (TMA 1-D) overlapped with the set-up instead of 14 rounds of LDG + STS
 #endif
@@ -137,7 +140,10 @@ struct Params {
 
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
-  constexpr int ROWS = (MODE == MODE_Z) ? 128 : 64;        // rows per tile = N of the MMA
+  // rows per tile = N of the MMA.  The issue path costs ~130 cycles per tcgen05.mma whatever its N (wait counters,
+  // NTT_TIMING: with N = 64 the issuer was busy 87 % of MODE_AB while the tensor pipe was 16 % active), so MODE_AB uses
+  // 128-row tiles like MODE_Z; MODE_H stays at 64 rows (its workers build the operand: not issue-bound)
+  constexpr int ROWS = (MODE == MODE_Z || (MODE == MODE_AB && NTT_AB_ROWS == 128)) ? 128 : 64;
   constexpr int KB = (MODE == MODE_Z) ? 8 : 4;             // K blocks (64 wide) per tile
   constexpr int NHALF = (MODE == MODE_Z) ? 1 : 2;          // 128-feature halves computed per tile
   constexpr uint32_t SLOT_BYTES = ROWS * 128;              // one K block of the activation tile
@@ -145,6 +151,8 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   constexpr uint32_t W_KBLK = (MODE == MODE_Z ? 128 : 256) * 128;   // bytes per K block of the weight image
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(ROWS >> 3) << 17) | ((128u >> 4) << 24);
   constexpr bool SPLIT = (MODE == MODE_AB || MODE == MODE_Z);
+  constexpr int TCOLS = NHALF * ROWS;                      // TMEM columns of one accumulator buffer: 128 or 256
+  constexpr int NACCM = 512 / TCOLS < NACC ? 512 / TCOLS : NACC;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   }
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
+    for (int i = 0; i < NACCM; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
 #if NTT_BULK_W
     mbar_init(bar_w, 1);
 #endif
@@ -217,10 +225,10 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
       mbar_wait(bar_w, 0u);                                  // weight image landed
 #endif
       for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
-        const int buf = it % NACC;
-        const int use = it / NACC;
+        const int buf = it % NACCM;
+        const int use = it / NACCM;
         if (use >= 1) NTWAIT(tw1, mbar_wait(bar_acce + 8 * buf, (uint32_t)((use - 1) & 1)));
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TCOLS);
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb, ++c) {
           const uint32_t slot = c % NSLOT;
@@ -280,7 +288,9 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     const int q = warp & 3, g = warp >> 2;
     const int fhalf = (MODE == MODE_Z) ? side : (g >> 1);
     const int feat = fhalf * 128 + q * 32 + lane;            // output feature of this thread (column of [M, 256])
-    const int rbase = (MODE == MODE_Z) ? g * 32 : (g & 1) * 32;
+    // row groups (32 rows) per warp: Z: one (g); AB/H: ROWS / 64 consecutive groups starting at (g & 1) * (ROWS / 64)
+    constexpr int RGW = (MODE == MODE_Z) ? 1 : ROWS / 64;
+    const int rbase = (MODE == MODE_Z) ? g * 32 : (g & 1) * RGW * 32;
     const float bias = vbias[feat];
     uint32_t cb = 0;
 
@@ -314,16 +324,22 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     };
 
     auto epilogue = [&](int tile, int it) {
-      const int buf = it % NACC;
-      NTWAIT(tw0, mbar_wait(bar_accf + 8 * buf, (uint32_t)((it / NACC) & 1)));
+      const int buf = it % NACCM;
+      NTWAIT(tw0, mbar_wait(bar_accf + 8 * buf, (uint32_t)((it / NACCM) & 1)));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + g * 32);
-      float v[32];
-      tmem_ld32_issue(taddr, v);
+      // accumulator column of (feature half hf, tile row r): buf * TCOLS + hf * ROWS + r
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                             (uint32_t)(buf * TCOLS + (MODE == MODE_Z ? 0 : fhalf * ROWS) + rbase);
+      float vv[RGW][32];
+#pragma unroll
+      for (int rr = 0; rr < RGW; ++rr) tmem_ld32_issue(taddr + (uint32_t)(rr * 32), vv[rr]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);
-      const int row0 = tile * ROWS + rbase;
+#pragma unroll
+      for (int rr = 0; rr < RGW; ++rr) {
+      const float* v = vv[rr];
+      const int row0 = tile * ROWS + rbase + rr * 32;
       if (MODE == MODE_AB) {
         __half* out = (side ? p.out1 : p.out0) + feat;
 #pragma unroll
@@ -356,6 +372,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
             h16[(size_t)m * H] = __float2half_rn(o);
           }
         }
+      }
       }
     };
 
@@ -416,7 +433,7 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
 int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah, __half* Bm, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
   ntt::Params p{};
-  p.M = M; p.ntiles = (M + 63) / 64; p.N = ctx->N;
+  p.M = M; p.ntiles = (M + NTT_AB_ROWS - 1) / NTT_AB_ROWS; p.N = ctx->N;
   p.X = h16; p.W0 = w.img_W1s; p.W1 = w.img_W1d; p.bias0 = w.b1eff; p.out0 = Ah; p.out1 = Bm;
   int half = ctx->num_sms / 2;
   if (half > p.ntiles) half = p.ntiles;
