@@ -210,18 +210,6 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = launch_image_pack(ctx, w.W2, 256, 0, 0.5f, w.img_W2h, s))) return rc;
     if ((rc = launch_image_pack_z(ctx, w.W3, AGG_UNSCALE, w.img_W3z0, w.img_W3z1, s))) return rc;
     if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, 64.f, w.img_Wc1s, s))) return rc;
-    {
-      float hb[H], hw[H];
-      CUDA_TRY(cudaMemcpyAsync(hb, w.b2, sizeof(hb), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaMemcpyAsync(hw, w.wa, sizeof(hw), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaStreamSynchronize(s));
-      for (int c = 0; c < H / 2; ++c) {
-        const __half2 b = __floats2half2_rn(0.5f * hb[2 * c], 0.5f * hb[2 * c + 1]);
-        const __half2 a = __floats2half2_rn(hw[2 * c], hw[2 * c + 1]);
-        memcpy(&w.b2h_host[c], &b, 4);
-        memcpy(&w.wah_host[c], &a, 4);
-      }
-    }
   }
   NEED("to_energy.0.weight", {H, 2 * H}); ctx->We = tmp;
   NEED("to_energy.1.weight", {H}); ctx->e_ln_w = tmp;

@@ -89,9 +89,6 @@ struct LayerW {
   __half* img_Wc1s;     // Wc1 x 2^6 (gated messages are spilled x 2^-6)
   __half* img_W3z0;     // [W3h | W3a x 2^6] rows 0-127, K = 512 (node_tc.cu MODE_Z)
   __half* img_W3z1;     // rows 128-255
-  // host copies for the edge kernel's parameter block (constant bank operands): b2/2 and wa as packed half2
-  uint32_t b2h_host[128];
-  uint32_t wah_host[128];
 };
 
 struct dfm_ctx {

@@ -2,18 +2,29 @@
 //   m = SiLU(W2 SiLU(u) + b2), gate, per-residue segment sum              (src/models/egnn.py:95-116, 139-148)
 //   u = A_i + B_j + radial * w1r + T[d, relpos] + T[omega, theta, phi]     (SURVEY App. A.5 / A.7 decomposition)
 //
-// One persistent CTA per SM, 28 warps (25 active):
-//   warps 0-15  producers: gather B_j / table rows (fp16, L2), form u/2 in packed half2, SiLU via tanh.approx.f16x2,
-//               write the 128 x 256 fp16 operand tile S into shared memory one 64-column K block at a time
-//   warp  24    MMA issuer: D[128 x 256] (TMEM, fp32) = S * (W2/2)^T, one tcgen05.commit per K block (frees that
-//               block for the next tile's build) and one per tile (accumulator ready)
-//   warps 16-23 epilogue: TMEM -> registers, + b2/2, SiLU in half2, gate logit, gate, 32-row column sums by
-//               shuffle transposition, segment sum of the two residues of the tile -> agg (fp32)
-// The fp16 weight image (128 KB) stays resident in shared memory; accumulators are double buffered in TMEM
-// (2 x 256 columns) so that build(t+1), MMA(t) and epilogue(t-1) overlap.
+// One persistent CTA per SM over a contiguous range of 128-row tiles (2 residues x 64 edge slots), 28 warps whose
+// registers are re-partitioned with setmaxnreg (72 / 88 / 40):
+//   warps 0-15  producers: table rows of every edge gathered into registers one K block ahead (L2), + A_i + the B_j row
+//               the loaders staged + radial * w1r, SiLU via tanh.approx.f16x2 in packed half2, written in place into
+//               the 128 x 256 fp16 operand tile S (SWIZZLE_128B, K-major), one 64-column K block at a time
+//   warps 25-26 loaders: cp.async the B_j rows of a K block straight into the S tile as soon as the previous tile's MMA
+//               has consumed that block
+//   warp  24    MMA issuer: one K = 16 MMA that sets the accumulator to b2/2 (constant 1/16 tile x bias tile, no-swizzle
+//               descriptors), then D[128 x 256] (TMEM, fp32) += S * (W2/2)^T: four tcgen05.mma per K block, one
+//               tcgen05.commit per K block (frees it for the next tile) and one per tile (accumulator ready)
+//   warps 16-23 epilogue: tcgen05.ld.16x256b fragments (a thread owns 4 rows x 16 column pairs of its warp's 32 x 128
+//               block), SiLU in half2, gate logit (16-product half2 chains -> fp32, shuffles over the 4 lanes of a row,
+//               two-half combine through shared memory), sigmoid gate, gate-weighted segment sum as in-thread HFMA2 +
+//               a 14-step shuffle reduction, two-quarter combine through shared memory -> agg16; the last layer also
+//               spills the gated messages of the ligand rows for the coordinate head and, when no energy is wanted,
+//               walks only the tiles that hold a ligand residue (Params::lig_only)
+// The fp16 weight image (128 KB, cp.async.bulk at start-up) stays resident in shared memory; accumulators are double
+// buffered in TMEM (2 x 256 columns) so that build(t+1), MMA(t) and epilogue(t-1) overlap.
 //
 // All operands are pre-halved at production (A, B, tables, w1r, W2, b2 carry a factor 1/2), because
-// SiLU(x) = h + h * tanh(h) with h = x/2: one MUFU and one HFMA2 per element pair.
+// SiLU(x) = h + h * tanh(h) with h = x/2: two MUFU (tanh.approx.f16x2 has no packed form) and one HFMA2 per element pair.
+// Build switches (-D...): EWS_TIMING (per-role wait cycles), EWS_EXP (diagnostic, wrong results), EWS_*_REGS, EWS_SLEEP_*,
+// EWS_FOLD, EWS_BIAS_MMA, EWS_PIN_ADDR, EWS_BULK_W; profiles/r01/README.md lists what each measured.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -31,12 +42,12 @@ constexpr uint32_t W_KBLK = 256 * 128;               // bytes per 64-wide K bloc
 constexpr uint32_t S_KBLK = TILE_M * 128;
 constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_S = W_BYTES;
-constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // b2/2 [256] half, wa [256] half, w1r' [256] half, (spare 512 B)
+constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // (1 KB spare), w1r' [256] half at + 1024, (512 B spare)
 constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [<=4 column groups][128 rows] float gate partials
 constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [2 tile parities][4 lane quarters][256] float column sums
 constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [16 producer warps][2 slots][8 rows] int4 edge metadata
 constexpr uint32_t OFF_JRING = OFF_META + 16 * 2 * 8 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
-constexpr uint32_t OFF_VEC32 = OFF_JRING + 2 * 2 * 128 * 4; // b2/2 [256] float, wa [256] float (fp32 epilogue)
+constexpr uint32_t OFF_VEC32 = OFF_JRING + 2 * 2 * 128 * 4; // fragment-ordered b2/2 and wa as half2: [2 halves][4 t%4][20-word rows] each
 constexpr uint32_t OFF_BAR = OFF_VEC32 + 2048;            // 16 mbarriers + tmem base
 // b2 folded into the accumulator by one extra K = 16 MMA per tile: A = [128 x 16] of 1/16, B = [256 x 16] with row n = b2[n]/2
 // (both K-major, no swizzle: 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row groups 256 B apart)
@@ -67,15 +78,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_EXP
 #define EWS_EXP 0      // diagnostic experiments (wrong results): 1 = B rows from row 0, 2 = table rows from row 0, 4 = no tanh
 #endif
-#ifndef EWS_EPI_FP32
-#define EWS_EPI_FP32 0  // epilogue SiLU and gate logit in fp32 (tanh.approx.f32), packed to half2 only for the gate / segment sum
-#endif
 #ifndef EWS_TIMING
 #define EWS_TIMING 0   // 1: accumulate cycles spent in barrier waits per role into Params::timing (diagnostic builds)
 #endif
-#ifndef EWS_ROW_INTERLEAVE
-#define EWS_ROW_INTERLEAVE 0   // (measured slower: 1.29 vs 1.21 ms) producer warp w builds slots {w&7, (w&7)+8, ...} of its residue instead of 8 consecutive slots:
-#endif                         // every warp gets the same mix of kNN slots (two table gathers) and far slots (one)
 #ifndef EWS_PIN_ADDR
 #define EWS_PIN_ADDR 1
 #endif
@@ -103,19 +108,6 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #endif
 #ifndef EWS_FOLD
 #define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
-#endif
-#ifndef EWS_EPI_V3
-#define EWS_EPI_V3 1      // epilogue on tcgen05.ld.16x256b fragments: a thread holds 4 rows x 16 column pairs, so the gated
-#endif                    // segment sum is mostly in-thread FMAs (14 shuffle steps instead of 63)
-static_assert(!EWS_BIAS_MMA || EWS_EPI_V3, "the bias MMA belongs to the fragment epilogue (the older epilogues add b2 themselves)");
-#ifndef EWS_EPI_PIPE
-#define EWS_EPI_PIPE 1    // epilogue: 8-column tcgen05.ld double buffered (next chunk in flight while this one is computed)
-#endif
-#ifndef EWS_EPI_CONST
-#define EWS_EPI_CONST 0   // epilogue: b2/2 and wa from the parameter block's constant bank instead of LDS (measured slower: LDC.64 pairs)
-#endif
-#ifndef EWS_USE_ALO
-#define EWS_USE_ALO 0     // carry A_i as fp16 hi + lo (1) or a single fp16 (0)
 #endif
 
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
@@ -170,31 +162,7 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
 // 16 lanes x 256 bit x 2: lane t gets, for the two 8-column blocks b = 0, 1 at [taddr]:
 //   r[4b + 0..1] = (row t/4,     columns 8b + 2(t%4) + {0,1}),  r[4b + 2..3] = (row t/4 + 8, same columns)
 // (layout measured with profiles/probes/tmem_ld_shapes.cu)
@@ -259,7 +227,6 @@ struct Params {
   const __half* Wimg;       // (W2 / 2) fp16 SW128 image
   const int4* emeta;        // [B*N, 64] {global row of j, Tdrp row, Totp row or -1, radial bits}
   const __half* Ahi;        // [B*N, 256] fp16((W1s h_i + b1)/2)
-  const __half* Alo;        // [B*N, 256] residual of the above
   const __half* Bm;         // [B*N, 256] fp16((W1d h_j)/2)
   const __half* Tdrp;       // pre-halved merged tables
   const __half* Totp;
@@ -269,8 +236,6 @@ struct Params {
   const float* ba;          // [1]
   __half* agg16;            // [B*N, 256] fp16(agg x 2^-6) out
   __half* mstar;            // [B*L, 64, 256] fp16 (m* x 2^-6), last layer only
-  uint32_t b2h[128];        // b2/2 as packed half2 (constant-bank operands of the epilogue)
-  uint32_t wah[128];        // wa as packed half2
   unsigned long long* timing;   // EWS_TIMING: [8] cycles {prod wait bfull, prod total, loader wait empty, loader total,
                                 //                        mma wait full, mma wait acce, epi wait accf, epi total}
 };
@@ -278,21 +243,6 @@ struct Params {
 constexpr float RAD_SCALE = 0.03125f;     // radial is carried as fp16(radial / 32); w1r' = 32 * w1r / 2
 constexpr float MSTAR_SCALE = 0.015625f;  // gated messages are carried x 2^-6 in fp16 (column sums stay < 65504)
 
-// 32 lanes x NR packed registers -> lane l ends with the lane-sums of registers 2l and 2l+1 in v[0], v[1]
-template <int NR>
-__device__ __forceinline__ void lane_transpose_sum_h2(uint32_t* v, int lane) {
-#pragma unroll
-  for (int o = 16, n = NR; o >= 1; o >>= 1, n >>= 1) {
-    const bool up = (lane & o) != 0;
-    const int half = n >> 1;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const uint32_t send = up ? v[i] : v[i + half];
-      const uint32_t keep = up ? v[i + half] : v[i];
-      v[i] = h2add(keep, __shfl_xor_sync(0xffffffffu, send, o));
-    }
-  }
-}
 
 // NR packed registers summed over the lanes that differ in the bits OHI .. OLO (powers of two, OHI >= OLO), halving the
 // register count at every step: with NR = 16, OHI = 16, OLO = 4 lane l ends with v[0], v[1] = sums of registers
@@ -316,9 +266,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  __half* vb2 = reinterpret_cast<__half*>(smem + OFF_VEC);         // b2/2
-  __half* vwa = vb2 + 256;
-  __half* vwr = vb2 + 512;                                          // 16 * w1r
+  __half* vwr = reinterpret_cast<__half*>(smem + OFF_VEC) + 512;   // 16 * w1r
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 144);
   const uint32_t bar_bfull = sbase + OFF_BAR + 96;      // [4] B_j rows of a K block have landed in the S tile
   const uint32_t bar_full = sbase + OFF_BAR;            // [4]
@@ -336,10 +284,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
 #endif
     if (tid < 256) {
-      vb2[tid] = __float2half_rn(0.5f * p.b2[tid]);
-      vwa[tid] = __float2half_rn(p.wa[tid]);
       vwr[tid] = __float2half_rn(p.w1r[tid] * (0.5f / RAD_SCALE));
-#if EWS_EPI_V3
       if (tid < 128) {
         // fragment order of the 16x256b epilogue: [column half][t % 4][8-column block j] -> column pair ch*64 + 4 j + (t%4)
         const int pr = (tid >> 6) * 64 + 4 * (tid & 15) + ((tid >> 4) & 3);
@@ -350,10 +295,6 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         reinterpret_cast<__half2*>(smem + OFF_VEC32)[slot] = b;
         reinterpret_cast<__half2*>(smem + OFF_VEC32)[160 + slot] = w;
       }
-#else
-      reinterpret_cast<float*>(smem + OFF_VEC32)[tid] = 0.5f * p.b2[tid];
-      reinterpret_cast<float*>(smem + OFF_VEC32)[256 + tid] = p.wa[tid];
-#endif
     }
   }
 #if EWS_BIAS_MMA
@@ -417,11 +358,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     // item n+1 are in flight while item n is computed (two register buffers), across K blocks and across tiles.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
     const int c8 = lane & 7, rsub = lane >> 3;
-#if EWS_ROW_INTERLEAVE
-    auto prow = [&](int idx) -> int { return (warp >> 3) * 64 + (warp & 7) + 8 * idx; };
-#else
     auto prow = [&](int idx) -> int { return warp * 8 + idx; };
-#endif
     const int4 pad_meta = make_int4(0, 40 * 66 + 32, -1, 0);
     // B_j is already in the S tile (loader warps, cp.async); this role gathers the two table rows of each edge into
     // registers one K block ahead (two buffers), forms u/2, applies SiLU and overwrites the 16-byte chunk in place.
@@ -637,23 +574,17 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
     const int e = warp - NPROD;
     const int q = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
     const int ch = e >> 2;             // column half
-    const int erow = q * 32 + lane;
     const int hn = q >> 1;             // residue of the tile this warp's rows belong to
     const int ecol = ((ch * 2 + (q & 1)) * 32 + lane) * 2;   // first of the 2 columns this thread writes in the final combine
     const float ba = p.ba[0];
-    const uint32_t vec_s = sbase + OFF_VEC + (uint32_t)ch * 256u;
-    const uint32_t vec32_s = sbase + OFF_VEC32 + (uint32_t)ch * 512u;
-    const uint32_t part_s = sbase + OFF_PART + (uint32_t)erow * 4u;
     unsigned long long tw0 = 0;
     const long long tstart = clock64();
     int it = 0;
-#if EWS_EPI_V3
     // Fragment layout: lane t = (rg = t >> 2, cq = t & 3) holds rows rr(k) = q*32 + rg + 8 k (k = 0..3) and, for every
     // 8-column block j = 0..15 of this warp's column half, the column pair 8 j + 2 cq + {0, 1}: m[k * 16 + j].
     const int rg = lane >> 2, cq = lane & 3;
     const uint32_t vx_s = sbase + OFF_VEC32 + (uint32_t)((ch * 4 + cq) * 20) * 4u;
     const uint32_t part_row_s = sbase + OFF_PART + (uint32_t)(q * 32 + rg) * 4u;      // + 32 k bytes for row k
-    (void)erow; (void)vec_s; (void)vec32_s; (void)part_s;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int buf = it & 1;
       const int node = phys(tile) * 2 + hn;
@@ -778,133 +709,6 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
       }
     }
-#else
-    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-      const int buf = it & 1;
-      const int node = phys(tile) * 2 + hn, k = erow & 63;
-      const bool valid = node < p.total_nodes && k < p.K;
-      TWAIT(tw0, mbar_wait<EWS_SLEEP_E>(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1)));
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 128);
-      uint32_t m[64];
-      float dot = 0.f;
-#if EWS_EPI_PIPE && !EWS_EPI_FP32
-      {
-        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        uint32_t accA[8], accB[8];
-        auto chunks = [&](auto chc) {
-          constexpr int CH = decltype(chc)::value;
-          tmem_ld8_issue(taddr, accA);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            uint32_t* cur = (c & 1) ? accB : accA;
-            uint32_t* nxt = (c & 1) ? accA : accB;
-            tmem_ld_wait8(cur);
-            if (c + 1 < 16) tmem_ld8_issue(taddr + (c + 1) * 8, nxt);
-#if EWS_EPI_CONST
-            const uint4 bb = make_uint4(p.b2h[CH * 64 + c * 4], p.b2h[CH * 64 + c * 4 + 1], p.b2h[CH * 64 + c * 4 + 2], p.b2h[CH * 64 + c * 4 + 3]);
-            const uint4 ww = make_uint4(p.wah[CH * 64 + c * 4], p.wah[CH * 64 + c * 4 + 1], p.wah[CH * 64 + c * 4 + 2], p.wah[CH * 64 + c * 4 + 3]);
-#else
-            const uint4 bb = lds128(vec_s + (uint32_t)(c * 8) * 2u);
-            const uint4 ww = lds128(vec_s + 512u + (uint32_t)(c * 8) * 2u);
-#endif
-            const uint32_t x0 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), bb.x));
-            const uint32_t x1 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), bb.y));
-            const uint32_t x2 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), bb.z));
-            const uint32_t x3 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), bb.w));
-            m[c * 4 + 0] = x0; m[c * 4 + 1] = x1; m[c * 4 + 2] = x2; m[c * 4 + 3] = x3;
-            d0 = h2fma(x0, ww.x, d0); d1 = h2fma(x1, ww.y, d1); d2 = h2fma(x2, ww.z, d2); d3 = h2fma(x3, ww.w, d3);
-            if ((c & 3) == 3) {   // 4 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
-              const float2 f0 = h2f2(h2add(d0, d1)), f1 = h2f2(h2add(d2, d3));
-              dot += (f0.x + f0.y) + (f1.x + f1.y);
-              d0 = d1 = d2 = d3 = 0;
-            }
-          }
-        };
-        if (ch == 0) chunks(std::integral_constant<int, 0>{}); else chunks(std::integral_constant<int, 1>{});
-      }
-#else
-      uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t acc[16];
-        tmem_ld16_issue(taddr + c * 16, acc);
-        tmem_ld_wait();
-        if (EWS_EPI_FP32) {
-          float dl = 0.f;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 bb = lds128(vec32_s + (uint32_t)(c * 16 + g * 4) * 4u);
-            const uint4 ww = lds128(vec32_s + 1024u + (uint32_t)(c * 16 + g * 4) * 4u);
-            float hh[4], mm[4];
-            hh[0] = __uint_as_float(acc[g * 4 + 0]) + __uint_as_float(bb.x);
-            hh[1] = __uint_as_float(acc[g * 4 + 1]) + __uint_as_float(bb.y);
-            hh[2] = __uint_as_float(acc[g * 4 + 2]) + __uint_as_float(bb.z);
-            hh[3] = __uint_as_float(acc[g * 4 + 3]) + __uint_as_float(bb.w);
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              float t;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hh[e2]));
-              mm[e2] = fmaf(hh[e2], t, hh[e2]);
-            }
-            dl = fmaf(mm[0], __uint_as_float(ww.x), dl); dl = fmaf(mm[1], __uint_as_float(ww.y), dl);
-            dl = fmaf(mm[2], __uint_as_float(ww.z), dl); dl = fmaf(mm[3], __uint_as_float(ww.w), dl);
-            m[c * 8 + g * 2 + 0] = f2h2(mm[0], mm[1]);
-            m[c * 8 + g * 2 + 1] = f2h2(mm[2], mm[3]);
-          }
-          dot += dl;
-        } else {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint4 bb = lds128(vec_s + (uint32_t)(c * 16 + g * 8) * 2u);
-          const uint4 ww = lds128(vec_s + 512u + (uint32_t)(c * 16 + g * 8) * 2u);
-          const uint32_t x0 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1])), bb.x));
-          const uint32_t x1 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3])), bb.y));
-          const uint32_t x2 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5])), bb.z));
-          const uint32_t x3 = h2silu(h2add(f2h2(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7])), bb.w));
-          m[c * 8 + g * 4 + 0] = x0; m[c * 8 + g * 4 + 1] = x1; m[c * 8 + g * 4 + 2] = x2; m[c * 8 + g * 4 + 3] = x3;
-          d0 = h2fma(x0, ww.x, d0); d1 = h2fma(x1, ww.y, d1); d2 = h2fma(x2, ww.z, d2); d3 = h2fma(x3, ww.w, d3);
-        }
-        if (c & 1) {        // 4 products per half2 lane, then out to fp32 (short fp16 chains keep the gate logit accurate)
-          const float2 f0 = h2f2(h2add(d0, d1)), f1 = h2f2(h2add(d2, d3));
-          dot += (f0.x + f0.y) + (f1.x + f1.y);
-          d0 = d1 = d2 = d3 = 0;
-        }
-        }
-      }
-#endif
-      tc_fence_before();
-      mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
-      stsf(part_s + (uint32_t)ch * 512u, dot);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the 2 column halves of this row quarter
-      const float tot = (ldsf(part_s) + ldsf(part_s + 512u)) + ba;
-      const float g = valid ? MSTAR_SCALE * __fdividef(1.f, 1.f + __expf(-tot)) : 0.f;
-      const uint32_t g2 = f2h2(g, g);
-#pragma unroll
-      for (int i = 0; i < 64; ++i) m[i] = h2mul(m[i], g2);
-      if (p.last && valid) {
-        const int b = node / p.N, i = node - b * p.N;
-        if (i >= p.R) {
-          uint4* dst = reinterpret_cast<uint4*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + k) * H + ch * 128);
-#pragma unroll
-          for (int v4 = 0; v4 < 16; ++v4) dst[v4] = make_uint4(m[v4 * 4], m[v4 * 4 + 1], m[v4 * 4 + 2], m[v4 * 4 + 3]);
-        }
-      }
-      lane_transpose_sum_h2<64>(m, lane);       // lane l: columns ch*128 + 4l .. 4l+3 summed over this warp's 32 rows
-      const uint32_t ag = sbase + OFF_AGG + (uint32_t)buf * 4096u;
-      {
-        const float2 s0 = h2f2(m[0]), s1 = h2f2(m[1]);
-        const uint32_t a0 = ag + (uint32_t)(q * 256 + ch * 128 + lane * 4) * 4u;
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(s0.x), "f"(s0.y), "f"(s1.x), "f"(s1.y) : "memory");
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(5 + hn) : "memory");     // the 4 warps that hold this residue's rows
-      if (node < p.total_nodes) {
-        const uint32_t a0 = ag + (uint32_t)((2 * hn) * 256 + ecol) * 4u;
-        // agg stays x 2^-6 in fp16 (the W3a image carries the 2^6): operand of node_tc.cu MODE_Z
-        *reinterpret_cast<uint32_t*>(p.agg16 + (size_t)node * H + ecol) = f2h2(ldsf(a0) + ldsf(a0 + 1024u), ldsf(a0 + 4u) + ldsf(a0 + 1028u));
-      }
-    }
-#endif
     if (EWS_TIMING && e == 0 && lane == 0) { atomicAdd(p.timing + 6, tw0); atomicAdd(p.timing + 7, (unsigned long long)(clock64() - tstart)); }
   }
   tc_fence_before();
@@ -932,13 +736,11 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   }
   p.Wimg = w.img_W2h;
   p.emeta = emeta;
-  p.Ahi = Ahi; p.Alo = nullptr;
+  p.Ahi = Ahi;
   p.Bm = reinterpret_cast<const __half*>(a.Bm);
   p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
   p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
   p.agg16 = agg16; p.mstar = a.mstar;
-  memcpy(p.b2h, w.b2h_host, sizeof(p.b2h));
-  memcpy(p.wah, w.wah_host, sizeof(p.wah));
 #if EWS_TIMING
   static unsigned long long* tbuf = nullptr;
   if (!tbuf) { CUDA_TRY(cudaMalloc(&tbuf, 64)); CUDA_TRY(cudaMemset(tbuf, 0, 64)); }
