@@ -17,6 +17,8 @@ What is restated (reference = Graylab/DFMDock @ e2fd4991, paths relative to /roo
   * randomize_pose / modify_coords / rot_compose / get_clash_force / Euler_Maruyama_sampler
                                            src/inference_base.py:311-468 (centre_mode 0)
                                            src/inference.py:213-370       (centre_mode 1)
+  * torch_reverse(ode=True) branch         src/utils/so3_diffuser.py:366-367, src/utils/r3_diffuser.py:53-54
+  * modify_aa_coords (all-atom output)     src/inference_base.py:354-364, src/inference.py:256-266
 
 The arithmetic is written "as the reference writes it" (dense N x N x 100 one-hot pair features,
 N^2-row embedding GEMMs, [R, L, 512] energy tensor) because this file is also the CPU baseline
