@@ -139,6 +139,28 @@ def test_generic_graph_kernel_equals_register_resident_kernels():
     assert torch.equal(a[0, :, 20:].sort(-1).values, b[0, :, 20:].sort(-1).values)
 
 
+@pytest.mark.parametrize("n_rec,n_lig", [(40, 30), (41, 30), (40, 31), (150, 151), (7, 66)])
+def test_forward_without_energy_head_equals_forward_with_it(n_rec, n_lig):
+    """Without DFM_WANT_ENERGY the last layer only walks the tiles that hold a ligand residue and skips the layer-5 node
+    update (both feed nothing but the energy head).  Forces and scores must not change by a single bit -- for even and
+    odd N and R (the ligand tile walk depends on the parity of b N + R) and for batches."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd, hp = synthetic_state_dict(1, 66), synthetic_hparams(66)
+    batch = synthetic_complex(n_rec, n_lig, seed=9)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([14.0, 0.0, 0.0])
+    model = _model(sd, hp, "fp16")
+    model.set_complex(batch)
+    g = torch.Generator().manual_seed(1)
+    lig = torch.stack([batch["lig_pos"] + torch.randn(1, 1, 3, generator=g) * 2 for _ in range(5)], 0)
+    t = torch.tensor([0.9, 0.7, 0.5, 0.3, 0.1])
+    a = {k: v.clone() for k, v in model.score(lig, t, seed=4, forward_index=2, want_energy=True).items()}
+    b = model.score(lig, t, seed=4, forward_index=2, want_energy=False)
+    for k in ("f", "tr_score", "rot_score"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.isfinite(a["energy"]).all()
+
+
 def test_large_complex_beyond_1024_residues():
     """N = 1300 (> 1024: generic graph kernel, the 1N2C regime): kNN block equals the exact 20 nearest residues, 60 distinct
     neighbours per residue, finite scores, batched == single."""
@@ -313,6 +335,35 @@ def test_sample_api_sharding_invariance_and_determinism():
         Rt = aa_to_mat(a["rot_update"][k:k + 1].cpu())[0]
         want = (x0 - c0) @ Rt.T + c0 + a["tr_update"][k].cpu()
         assert max_abs(a["lig_pos"][k].cpu(), want) <= 2e-3 * max(1.0, float(want.abs().max()))
+
+
+def test_full_benchmark_size_sampling_is_deterministic_and_shard_invariant():
+    """BASELINE config #3 at full size (2x150 residues, 256 trajectories; 5 steps): the same seed gives the same bits, a
+    trajectory's result does not depend on which batch it runs in (256 together == 96 + 160 apart), and the accumulated
+    rigid transform reproduces every final pose (size-independent property of the path)."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    from oracle.dfmdock_oracle import aa_to_mat
+    sd, hp = synthetic_state_dict(0, 66), synthetic_hparams(66)
+    batch = synthetic_complex(150, 150, seed=0)
+    model = _model(sd, hp, "fp16")
+    model.set_complex(batch)
+    a = {k: v.clone() for k, v in model.sample(batch["lig_pos"], 256, num_steps=5, seed=3).items()}
+    b = model.sample(batch["lig_pos"], 256, num_steps=5, seed=3)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.isfinite(a[k].float()).all(), k
+    lo = {k: v.clone() for k, v in model.sample(batch["lig_pos"], 96, num_steps=5, seed=3, stream_base=0).items()}
+    hi = model.sample(batch["lig_pos"], 160, num_steps=5, seed=3, stream_base=96)
+    for k in a:
+        assert torch.equal(torch.cat([lo[k], hi[k]], 0), a[k]), k
+    x0 = batch["lig_pos"]
+    c0 = x0[:, 1].mean(0)
+    Rt = aa_to_mat(a["rot_update"].cpu())                       # [256,3,3]
+    want = torch.einsum("nac,bdc->bnad", x0 - c0, Rt) + c0 + a["tr_update"].cpu()[:, None, None, :]
+    err = (a["lig_pos"].cpu() - want).abs().amax(dim=(1, 2, 3))
+    scale = want.abs().amax(dim=(1, 2, 3)).clamp(min=1.0)
+    assert float((err / scale).max()) <= 2e-3
 
 
 def test_reference_signature_sampler_runs():
