@@ -34,6 +34,15 @@ void dfm_set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
+// cudaFuncSetAttribute is per device: remember per kernel (one static mask per call site) which devices are done, so
+// that several contexts on different GPUs of one process all get their dynamic shared memory limit raised
+__host__ inline bool dfm_once_per_device(unsigned long long& mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 #define LAUNCH_CHECK(ctx)                                                                   \
   do {                                                                                      \
     (ctx)->launches++;                                                                      \

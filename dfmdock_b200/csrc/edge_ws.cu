@@ -756,10 +756,9 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
     }
   }
 #endif
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
-    attr = true;
   }
   int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;

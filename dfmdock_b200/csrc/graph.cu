@@ -451,10 +451,9 @@ int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const 
     dfm_set_error("complex too large for the graph kernel (N=%d)", N);
     return DFM_EINVAL;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(k_graph<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const long rows = (long)B * N;
   const int grid = (int)((rows + WARPS - 1) / WARPS);

@@ -400,10 +400,9 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
 
 template <int MODE>
 static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(k_nodeT<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
-    attr = true;
   }
   if (grid <= 0) return 0;
 #if NTT_TIMING

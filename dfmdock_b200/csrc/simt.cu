@@ -79,10 +79,9 @@ __global__ void __launch_bounds__(256) k_linear_simt(LinearArgs a) {
 
 int launch_linear_simt(dfm_ctx* ctx, const LinearArgs& a, cudaStream_t s) {
   const size_t smem = (64 * LDS + 16 * 256) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(k_linear_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   k_linear_simt<<<(a.M + 63) / 64, 256, smem, s>>>(a);
   LAUNCH_CHECK(ctx);
@@ -208,10 +207,9 @@ k_edge_simt(EdgeArgs a, const float* __restrict__ T, const float* __restrict__ w
 int launch_edge_simt(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   const LayerW& w = ctx->layer[a.layer];
   const size_t smem = (64 * LDS + 16 * 256) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(k_edge_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   k_edge_simt<<<a.B * a.N, 256, smem, s>>>(a, w.T32, w.w1r, w.W2, w.b2, w.wa, w.ba, w.Wc1, w.bc1, w.wc2);
   LAUNCH_CHECK(ctx);

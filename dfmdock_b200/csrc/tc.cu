@@ -534,10 +534,9 @@ __global__ void __launch_bounds__(NT, 1) k_tc(const Params p) {
 
 template <int MODE, int VAR = 0>
 static int launch(dfm_ctx* ctx, const Params& p, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
     CUDA_TRY(cudaFuncSetAttribute(k_tc<MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
-    attr = true;
   }
   const int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;
