@@ -138,6 +138,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples), "source": self.source}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    communicator), so everything that is not the result line is sent to stderr: fd 1 is re-pointed at fd 2 and the line
+    is written to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def make_workload():
     from dfmdock_b200.features import synthetic_complex
     from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
@@ -182,7 +205,7 @@ def run_reference(args):
                          "sample": "%d trajectories x %d reverse steps, N=300, %.1f s wall" % (traj, steps, wall)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_cuda(args):
@@ -353,7 +376,7 @@ def run_cuda(args):
             "cpu_baseline": cpu,
             "full_job": full_job,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -368,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-job", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
