@@ -101,6 +101,9 @@ __device__ __forceinline__ float silu_tanh(float x) {
 
 enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2 };
 
+#ifndef NTT_Z_ROWS
+#define NTT_Z_ROWS 128    // rows per MODE_Z tile (128 or 256)
+#endif
 #ifndef NTT_AB_ROWS
 #define NTT_AB_ROWS 128   // rows per MODE_AB tile (64 or 128)
 #endif
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   // rows per tile = N of the MMA.  The issue path costs ~130 cycles per tcgen05.mma whatever its N (wait counters,
   // NTT_TIMING: with N = 64 the issuer was busy 87 % of MODE_AB while the tensor pipe was 16 % active), so MODE_AB uses
   // 128-row tiles like MODE_Z; MODE_H stays at 64 rows (its workers build the operand: not issue-bound)
-  constexpr int ROWS = (MODE == MODE_Z || (MODE == MODE_AB && NTT_AB_ROWS == 128)) ? 128 : 64;
+  constexpr int ROWS = (MODE == MODE_Z) ? NTT_Z_ROWS : (MODE == MODE_AB && NTT_AB_ROWS == 128) ? 128 : 64;
   constexpr int KB = (MODE == MODE_Z) ? 8 : 4;             // K blocks (64 wide) per tile
   constexpr int NHALF = (MODE == MODE_Z) ? 1 : 2;          // 128-feature halves computed per tile
   constexpr uint32_t SLOT_BYTES = ROWS * 128;              // one K block of the activation tile
@@ -289,8 +292,8 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     const int fhalf = (MODE == MODE_Z) ? side : (g >> 1);
     const int feat = fhalf * 128 + q * 32 + lane;            // output feature of this thread (column of [M, 256])
     // row groups (32 rows) per warp: Z: one (g); AB/H: ROWS / 64 consecutive groups starting at (g & 1) * (ROWS / 64)
-    constexpr int RGW = (MODE == MODE_Z) ? 1 : ROWS / 64;
-    const int rbase = (MODE == MODE_Z) ? g * 32 : (g & 1) * RGW * 32;
+    constexpr int RGW = (MODE == MODE_Z) ? ROWS / 128 : ROWS / 64;
+    const int rbase = (MODE == MODE_Z) ? g * RGW * 32 : (g & 1) * RGW * 32;
     const float bias = vbias[feat];
     uint32_t cb = 0;
 
@@ -443,7 +446,7 @@ int launch_node_ab(dfm_ctx* ctx, int layer, int M, const __half* h16, __half* Ah
 int launch_node_z(dfm_ctx* ctx, int layer, int M, const __half* h16, const __half* agg16, float* z, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
   ntt::Params p{};
-  p.M = M; p.ntiles = (M + 127) / 128; p.N = ctx->N;
+  p.M = M; p.ntiles = (M + NTT_Z_ROWS - 1) / NTT_Z_ROWS; p.N = ctx->N;
   p.X = h16; p.X2 = agg16; p.W0 = w.img_W3z0; p.W1 = w.img_W3z1; p.bias0 = w.b3; p.out32 = z;
   int half = ctx->num_sms / 2;
   if (half > p.ntiles) half = p.ntiles;
