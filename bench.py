@@ -5,9 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores (oracle port)
 
 Workload (config #3 of BASELINE.json, the one the metric is quoted on): synthetic 2x150-residue complex, 256
-trajectories per GPU advancing in lock step, random-init weights of the shipped architecture.  A "step" = one
-reverse-diffusion step of all 256 trajectories (score-network forward + SO(3)xR^3 Euler-Maruyama update) =
-256 pose-steps.  value = pose-steps/s over all GPUs (weak scaling: 256 trajectories per GPU).
+trajectories per GPU advancing in lock step, weights/pinder_0.ckpt (oracle/_ref/pinder_0.pt travels with the repo
+snapshot; seeded random weights of the same architecture only if it is absent -- config.weights says which ran).
+A "step" = one reverse-diffusion step of all 256 trajectories (score-network forward + SO(3)xR^3 Euler-Maruyama
+update) = 256 pose-steps, timed on poses IN CONTACT in the second half of the schedule (t <= 0.5: every inter-chain
+pair inside 22 A takes the angle-table gathers -- the expensive regime; far starts are cheaper and are part of
+full_job).  value = pose-steps/s over all GPUs.  Default scaling is weak (256 trajectories per GPU);
+--scaling strong splits 256 trajectories over the GPUs, and every multi-GPU line carries the strong
+figure next to the weak one under "strong_scaling".
 
 Keys beyond the base contract:
   e2e          same metric through the public Python API with HOST buffers (pinned H2D of poses/times, D2H of poses/scores per step)
@@ -15,6 +20,7 @@ Keys beyond the base contract:
                measured dense fp16/bf16 tensor peak in MEASURED_PEAKS.json (sustained figure: kernel timed inside a long step)
   cpu_baseline oracle port (the reference's algorithm, torch CPU ops as the reference writes them) on a bounded sample
   full_job     one complete config-#3 job (256 trajectories x 100 steps incl. random init and the final energy forward)
+  other_configs  (N=1) complete jobs of BASELINE configs #2 (1QA9, 40 x 40, pinder_0, clash force) and #4 (2x400, 64 x 100)
 """
 import argparse
 import json
@@ -161,11 +167,42 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
-def make_workload():
-    from dfmdock_b200.features import synthetic_complex
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def load_weights():
+    """-> (state_dict, hparams, positional width, description).  The shipped weights/pinder_0.ckpt when oracle/_ref holds
+    its re-serialised copy (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot), else seeded random weights."""
+    import torch
     from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
-    batch = synthetic_complex(N_REC, N_LIG, seed=0, pos_width=66)
-    return synthetic_state_dict(0, 66), synthetic_hparams(66), batch
+    p = os.path.join(REF_DIR, "pinder_0.pt")
+    if os.path.exists(p) and not os.environ.get("DFM_BENCH_SYNTHETIC_WEIGHTS"):
+        ck = torch.load(p, weights_only=False)
+        return ck["state_dict"], ck["hparams"], 67, "weights/pinder_0.ckpt (trained, 3.57 M parameters)"
+    return synthetic_state_dict(0, 66), synthetic_hparams(66), 66, "seeded random weights of the shipped architecture (oracle/_ref/pinder_0.pt absent)"
+
+
+def make_workload(n_rec=N_REC, n_lig=N_LIG):
+    from dfmdock_b200.features import synthetic_complex
+    sd, hp, width, desc = load_weights()
+    batch = synthetic_complex(n_rec, n_lig, seed=0, pos_width=width)
+    return sd, hp, batch, desc
+
+
+def contact_poses(lig0, n, seed=0, max_angle=0.6, tr_std=3.0):
+    """n rigid copies of the generator's ligand pose (chains in contact, SURVEY 8d: +25 A along x): rotation about the CA
+    centroid by a random axis-angle (<= max_angle rad) + N(0, tr_std^2) translation per trajectory."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    aa = torch.randn(n, 3, generator=g)
+    ang = torch.rand(n, 1, generator=g) * max_angle
+    ax = aa / aa.norm(dim=-1, keepdim=True)
+    K = torch.zeros(n, 3, 3)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+    Rm = torch.eye(3)[None] + torch.sin(ang)[:, :, None] * K + (1 - torch.cos(ang))[:, :, None] * (K @ K)   # Rodrigues
+    c = lig0[:, 1].mean(0)
+    tr = torch.randn(n, 1, 1, 3, generator=g) * tr_std
+    return torch.einsum("lac,ndc->nlad", lig0 - c, Rm) + c + tr
 
 
 def cpu_reference_throughput(num_traj, num_steps, threads=None):
@@ -174,7 +211,7 @@ def cpu_reference_throughput(num_traj, num_steps, threads=None):
     from oracle import dfmdock_oracle as orc
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
     torch.set_num_threads(threads or os.cpu_count() or 1)
-    sd, hp, batch = make_workload()
+    sd, hp, batch, _ = make_workload()
     net = orc.OracleNet(sd, cut_off=hp["model"]["cut_off"])
     import numpy as np
     np.random.seed(0)
@@ -195,17 +232,62 @@ def run_reference(args):
     steps = max(2, min(args.steps, 10))
     traj = 2
     value, wall, cores = cpu_reference_throughput(traj, steps)
+    desc = load_weights()[3]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "synthetic 2x150-residue complex, reference algorithm on host CPU (oracle port), serial trajectories at batch 1",
-                   "n_res": N_REC + N_LIG, "sample": "%d trajectories x %d steps (+ final forward each)" % (traj, steps)},
+                   "n_res": N_REC + N_LIG, "weights": desc,
+                   "sample": "%d trajectories x %d steps (+ final forward each)" % (traj, steps)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d trajectories x %d reverse steps, N=300, %.1f s wall" % (traj, steps, wall)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+DTYPE = ("f16: tcgen05 operands, inter-kernel activations and the packed-half2 SIMT math of the edge kernel (both SiLUs, gate "
+         "logit partial sums, gated 60-edge segment sum) are fp16; MMA accumulators, GraphNorm statistics, the residual "
+         "stream h and all geometry are f32")
+TOLERANCE = "1e-2 relative (L2) on forces / scores vs the fp32 oracle at this configuration (tests/test_gpu_configs.py; measured worst printed there)"
+
+
+def time_full_job(model, batch, T, S, seed, stream_base=0, **kw):
+    """One complete dfm_sample job with CUDA events -> (milliseconds, result dict)."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = model.sample(batch["lig_pos"], T, num_steps=S, seed=seed, stream_base=stream_base, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), res
+
+
+def other_configs(dev, sd, hp):
+    """BASELINE configs #2 and #4 as complete jobs on one GPU (parity-test sizes, reported beside the bench line)."""
+    import torch
+    from dfmdock_b200 import Score_Model
+    from dfmdock_b200.features import batch_from_record, synthetic_complex
+    out = {}
+    model = Score_Model(sd, hp, precision="fp16").to(dev)
+    rec_path = os.path.join(REF_DIR, "db5_1QA9.pt")
+    if os.path.exists(rec_path):
+        batch = batch_from_record(torch.load(rec_path, weights_only=False), pos_width=model.pos_width)
+        model.set_complex(batch)
+        kw = dict(use_clash_force=True, centre_mode=1)
+        time_full_job(model, batch, 40, 3, 1, **kw)
+        ms, res = time_full_job(model, batch, 40, 40, 2, **kw)
+        out["c2"] = {"workload": "db5 1QA9 (N=197), 40 trajectories x 40 steps, clash force (src/inference.py defaults)",
+                     "wall_ms": ms, "poses_per_s": 40 * 40 / (ms * 1e-3), "us_per_lockstep_step": ms * 1e3 / 41,
+                     "best_energy": float(res["energy"].min())}
+    batch = synthetic_complex(400, 400, seed=0, pos_width=model.pos_width)
+    model.set_complex(batch)
+    time_full_job(model, batch, 64, 3, 1)
+    ms, res = time_full_job(model, batch, 64, 100, 2)
+    out["c4"] = {"workload": "synthetic 2x400 residues, 64 trajectories x 100 steps", "wall_ms": ms,
+                 "poses_per_s": 64 * 100 / (ms * 1e-3), "best_energy": float(res["energy"].min())}
+    return out
 
 
 def run_cuda(args):
@@ -223,27 +305,19 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    sd, hp, batch = make_workload()
+    sd, hp, batch, wdesc = make_workload()
     model = Score_Model(sd, hp, precision="fp16").to(dev)
     model.set_complex(batch)
-    B, L, N = TRAJ_PER_GPU, N_LIG, N_REC + N_LIG
+    L, N = N_LIG, N_REC + N_LIG
     S = FULL_STEPS
     ts = torch.linspace(1.0, 1e-3, S)
     dt = float(ts[0] - ts[1])
-    base = rank * B          # global trajectory index -> Philox subsequence (results independent of the number of GPUs)
+    half = S // 2
 
-    lig, tr_u, rot_u = model.randomize_pose(batch["lig_pos"], B, seed=args.seed, stream_base=base)
-    t_dev = torch.empty(B, device=dev)
-    state = {"i": 0}
-
-    def one_step():
-        i = state["i"] % (S - 1)            # never the noise-free last step: steady-state steps only
-        t = float(ts[i])
-        t_dev.fill_(t)
-        o = model.score(lig, t_dev, seed=args.seed, stream_base=base, forward_index=state["i"])
-        model.reverse_step(lig, rot_u, tr_u, o["tr_score"], o["rot_score"], t, dt, 0.5, 0.5, seed=args.seed,
-                           stream_base=base, step_index=state["i"])
-        state["i"] += 1
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -251,40 +325,74 @@ def run_cuda(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    sync_all()
+    def make_state(B, base):
+        """B trajectories of this rank in contact (global trajectory index base + b -> pose seed and Philox subsequence)."""
+        lig = contact_poses(batch["lig_pos"], B, seed=1000 + base).to(dev)
+        return {"B": B, "base": base, "lig": lig, "tr_u": torch.zeros(B, 3, device=dev), "rot_u": torch.zeros(B, 3, device=dev),
+                "t": torch.empty(B, device=dev), "i": 0}
 
-    # ---- device-resident timed region ------------------------------------------------------------
-    try:
-        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    except Exception:
-        gpu_uuid = None
-    model.profile_enable(args.steps * 8)
-    launches0 = model.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank, gpu_uuid) as clocks:
+    def one_step(st):
+        i = half + st["i"] % (S - 1 - half)      # second half of the schedule, never the noise-free last step
+        t = float(ts[i])
+        st["t"].fill_(t)
+        o = model.score(st["lig"], st["t"], seed=args.seed, stream_base=st["base"], forward_index=st["i"])
+        model.reverse_step(st["lig"], st["rot_u"], st["tr_u"], o["tr_score"], o["rot_score"], t, dt, 0.5, 0.5, seed=args.seed,
+                           stream_base=st["base"], step_index=st["i"])
+        st["i"] += 1
+
+    def timed_region(st, steps, profile):
+        """steps lock-step steps + the path's only collective, CUDA events, max over ranks -> (ms, launches, clocks, edge ms, edge n)."""
+        for _ in range(max(args.warmup, 3)):
+            one_step(st)
         sync_all()
-        e0.record()
-        for _ in range(args.steps):
-            one_step()
+        if profile:
+            model.profile_enable(steps * 8)
+        launches0 = model.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank, gpu_uuid) as clocks:
+            sync_all()
+            e0.record()
+            for _ in range(steps):
+                one_step(st)
+            if world > 1:
+                table = torch.cat([st["rot_u"], st["tr_u"], torch.zeros(st["B"], 2, device=dev)], dim=1)
+                full = torch.empty(world * st["B"], 8, device=dev)
+                dist.all_gather_into_tensor(full, table)         # the path's only collective: [T_local, 8] result rows
+            e1.record()
+            sync_all()
+        ms = e0.elapsed_time(e1)
+        launches = model.launch_count - launches0
+        edge_ms, edge_n = (0.0, 0)
+        if profile:
+            edge_ms, edge_n = model.profile_read()
+            model.profile_enable(0)
+        tmax = torch.tensor([ms], device=dev)
         if world > 1:
-            table = torch.cat([rot_u, tr_u, torch.zeros(B, 2, device=dev)], dim=1)
-            full = torch.empty(world * B, 8, device=dev)
-            dist.all_gather_into_tensor(full, table)         # the path's only collective: [T_local, 8] result rows
-        e1.record()
-        sync_all()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = model.launch_count - launches0
-    edge_ms, edge_n = model.profile_read()
-    model.profile_enable(0)
-    tmax = torch.tensor([elapsed_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(tmax.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return float(tmax.item()), launches, clocks.summary(), edge_ms, edge_n
+
+    strong = args.scaling == "strong"
+    B_weak = TRAJ_PER_GPU
+    lo_s = rank * TRAJ_PER_GPU // world
+    B_strong = (rank + 1) * TRAJ_PER_GPU // world - lo_s
+    # ---- primary timed region (device resident) ------------------------------------------------------
+    B = B_strong if strong else B_weak
+    base = lo_s if strong else rank * B_weak
+    st = make_state(B, base)
+    elapsed_ms, launches, clk, edge_ms, edge_n = timed_region(st, args.steps, True)
+    total_traj = TRAJ_PER_GPU if strong else world * B_weak
+    value = total_traj * args.steps / (elapsed_ms * 1e-3)
+    # ---- the other scaling mode beside it (multi-GPU lines only; at N = 1 the two coincide) ----------------
+    strong_line = {"trajectories_total": TRAJ_PER_GPU, "trajectories_per_gpu": B_strong, "value": value if (strong or world == 1) else None,
+                   "unit": UNIT, "ms_per_step": elapsed_ms / args.steps if (strong or world == 1) else None}
+    if world > 1 and not strong:
+        st2 = make_state(B_strong, lo_s)
+        ms2, _, _, _, _ = timed_region(st2, args.steps, False)
+        strong_line.update(value=TRAJ_PER_GPU * args.steps / (ms2 * 1e-3), ms_per_step=ms2 / args.steps)
+        del st2
 
     # ---- end-to-end through the public API with host buffers -----------------------------------------
+    lig, tr_u, rot_u = st["lig"], st["tr_u"], st["rot_u"]
     lig_host = torch.empty(B, L, 3, 3).pin_memory()
     t_host = torch.empty(B).pin_memory()
     out_host = torch.empty(B, L, 3, 3).pin_memory()
@@ -293,7 +401,7 @@ def run_cuda(args):
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step(k):
-        t = float(ts[k % (S - 1)])
+        t = float(ts[half + k % (S - 1 - half)])
         t_host.fill_(t)
         lig_d = lig_host.to(dev, non_blocking=True)
         t_d = t_host.to(dev, non_blocking=True)
@@ -315,23 +423,25 @@ def run_cuda(args):
     te = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(te.item())
+    e2e_value = total_traj * e2e_steps / float(te.item())
 
-    # ---- one complete config-#3 job (256 x 100 with init + final energy forward) ------------------------
+    # ---- one complete config-#3 job (random init far apart, 100 steps, final energy forward) ----------------
     full_job = None
     if not args.no_full_job:
         sync_all()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        res = model.sample(batch["lig_pos"], B, num_steps=FULL_STEPS, seed=args.seed, stream_base=base)
-        f1.record()
-        sync_all()
-        fj = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        ms, res = time_full_job(model, batch, B, FULL_STEPS, args.seed, stream_base=base)
+        fj = torch.tensor([ms], device=dev)
+        emin = res["energy"].min().reshape(1)
         if world > 1:
             dist.all_reduce(fj, op=dist.ReduceOp.MAX)
-        full_job = {"trajectories": world * B, "steps": FULL_STEPS, "wall_s": float(fj.item()) * 1e-3,
-                    "poses_per_s": world * B * FULL_STEPS / (float(fj.item()) * 1e-3),
-                    "best_energy": float(res["energy"].min().item())}
+            dist.all_reduce(emin, op=dist.ReduceOp.MIN)
+        full_job = {"trajectories": total_traj, "steps": FULL_STEPS, "wall_s": float(fj.item()) * 1e-3,
+                    "poses_per_s": total_traj * FULL_STEPS / (float(fj.item()) * 1e-3),
+                    "best_energy": float(emin.item())}
+
+    others = None
+    if world == 1 and not args.no_other_configs:
+        others = other_configs(dev, sd, hp)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -353,18 +463,18 @@ def run_cuda(args):
         step_flops = algorithmic_flops_per_pose_step(N) * B
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "synthetic 2x150-residue complex (BASELINE config #3), %d trajectories per GPU in lock step" % B,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "synthetic 2x150-residue complex (BASELINE config #3), %d trajectories %s in lock step, poses in contact, "
+                                   "second half of the 100-step schedule" % (TRAJ_PER_GPU, "in total" if strong else "per GPU"),
                        "n_res": N, "trajectories_per_gpu": B, "edges_per_step_per_gpu": 60 * N * B,
-                       "weights": "random-init, shipped architecture (H=256, depth 6); the scores are not physical, so the poses drift "
-                                  "apart and the final energy head sees no pair inside its 20 A cut-off (full_job.best_energy = 0)",
-                       "l2": "per-step working set ~%.1f GB per GPU, far larger than the 126 MB L2; no explicit flush" % (1.9),
+                       "weights": wdesc, "dtype_detail": DTYPE, "tolerance": TOLERANCE,
+                       "l2": "per-step working set ~%.1f GB per GPU, far larger than the 126 MB L2; no explicit flush" % (1.9 * B / 256.0),
                        "parallelism": "trajectory-sharded x%d, one all-gather of [T,8] at the end" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * L * 36 + B * 4, "d2h_bytes_per_step": B * L * 36 + B * 24,
                     "steps": e2e_steps},
             "gpu_launches": launches,
-            "clocks": clocks.summary(),
+            "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "ews::k_edge_ws (warp-specialised fused edge MLP, tcgen05)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
                          "traffic": traffic, "peak_source": peaks["source"], "kernel_ms_per_launch": edge_avg_ms,
@@ -373,8 +483,10 @@ def run_cuda(args):
                                        "(5 x all edges + 1 x the ligand residues' edges = %.4f of 6 full launches)" % executed,
                          "kernel_share_of_step": (edge_ms / elapsed_ms) if edge_n else None,
                          "whole_step_tflops": step_flops / (elapsed_ms / args.steps * 1e-3) / 1e12},
+            "strong_scaling": strong_line,
             "cpu_baseline": cpu,
             "full_job": full_job,
+            "other_configs": others,
         }
         emit(line)
     if world > 1:
@@ -390,6 +502,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-job", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 256 trajectories per GPU (default); strong: 256 trajectories split over the GPUs (SURVEY 8e)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

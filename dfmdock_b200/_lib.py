@@ -25,6 +25,8 @@ PROTOTYPES = {
     "dfm_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
     "dfm_finalize_weights": (c_int, [c_void_p, c_float, c_void_p]),
     "dfm_set_complex": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "dfm_set_schedule": (c_int, [c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "dfm_interface_logits": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dfm_set_receptor_pose": (c_int, [c_void_p, c_void_p, c_void_p]),
     "dfm_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "dfm_edges_per_node": (c_int, [c_void_p]),

@@ -89,7 +89,6 @@ extern "C" int dfm_create(dfm_ctx** out, int device) {
   dfm_ctx* c = new dfm_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("DFM_EDGE_KERNEL")) c->edge_kernel = atoi(e);
   if (dfm_upload_bin_edges() != 0) {
     delete c;
     dfm_set_error("dfm_create: cannot upload bin edges");
@@ -189,24 +188,16 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     }
     const size_t trows = NSPATIAL + ctx->P;
     if ((rc = dev_alloc(ctx, &w.T32, trows * H))) return rc;
-    if ((rc = dev_alloc(ctx, &w.T16, trows * H))) return rc;
-    if ((rc = dev_alloc(ctx, &w.Tdrp16, (size_t)2 * 40 * 66 * H))) return rc;
-    if ((rc = dev_alloc(ctx, &w.Totp16, (size_t)24 * 24 * 12 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.Tdrp16h, (size_t)2 * 40 * 66 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.Totp16h, (size_t)24 * 24 * 12 * H))) return rc;
     if ((rc = dev_alloc(ctx, &w.w1r, H))) return rc;
     if ((rc = dev_alloc(ctx, &w.b1eff, H))) return rc;
-    __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W2, &w.img_W3h, &w.img_W3a, &w.img_W4, &w.img_Wc1, &w.img_W2h,
-                       &w.img_Wc1s, &w.img_W3z0, &w.img_W3z1};
+    __half** imgs[] = {&w.img_W1s, &w.img_W1d, &w.img_W4, &w.img_W2h, &w.img_Wc1s, &w.img_W3z0, &w.img_W3z1};
     for (auto pp : imgs) if ((rc = dev_alloc(ctx, pp, (size_t)H * H))) return rc;
     if ((rc = launch_pair_table(ctx, l, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W1, 641, 0, 1.f, w.img_W1s, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W1, 641, 256, 1.f, w.img_W1d, s))) return rc;
-    if ((rc = launch_image_pack(ctx, w.W2, 256, 0, S_UNSCALE, w.img_W2, s))) return rc;
-    if ((rc = launch_image_pack(ctx, w.W3, 512, 0, 1.f, w.img_W3h, s))) return rc;
-    if ((rc = launch_image_pack(ctx, w.W3, 512, 256, AGG_UNSCALE, w.img_W3a, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W4, 256, 0, 1.f, w.img_W4, s))) return rc;
-    if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, S_UNSCALE, w.img_Wc1, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W2, 256, 0, 0.5f, w.img_W2h, s))) return rc;
     if ((rc = launch_image_pack_z(ctx, w.W3, AGG_UNSCALE, w.img_W3z0, w.img_W3z1, s))) return rc;
     if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, 64.f, w.img_Wc1s, s))) return rc;
@@ -227,6 +218,21 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     NEED(std::string(sc[q]) + ".1.weight", {DFM_INNER_DIM}); ctx->sc_lnw[q] = tmp;
     NEED(std::string(sc[q]) + ".1.bias", {DFM_INNER_DIM}); ctx->sc_lnb[q] = tmp;
     NEED(std::string(sc[q]) + ".4.weight", {1, DFM_INNER_DIM}); ctx->sc_w2[q] = tmp;
+  }
+  // to_ires.* is optional (dead at inference): present -> dfm_interface_logits works
+  ctx->ires_W1t = ctx->ires_W3t = nullptr;
+  if (ctx->w.count("to_ires.0.weight")) {
+    const float *w1, *w3;
+    NEED("to_ires.0.weight", {512, H}); w1 = tmp;
+    NEED("to_ires.0.bias", {512}); ctx->ires_b1 = tmp;
+    NEED("to_ires.2.weight", {512, 512}); w3 = tmp;
+    NEED("to_ires.2.bias", {512}); ctx->ires_b3 = tmp;
+    NEED("to_ires.4.weight", {1, 512}); ctx->ires_w5 = tmp;
+    NEED("to_ires.4.bias", {1}); ctx->ires_b5 = tmp;
+    if ((rc = dev_alloc(ctx, &ctx->ires_W1t, (size_t)512 * H))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ires_W3t, (size_t)512 * 512))) return rc;
+    if ((rc = launch_transpose(ctx, w1, 512, H, ctx->ires_W1t, s))) return rc;
+    if ((rc = launch_transpose(ctx, w3, 512, 512, ctx->ires_W3t, s))) return rc;
   }
 #undef NEED
   ctx->cut_off = cut_off;
@@ -257,17 +263,25 @@ extern "C" int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const floa
   ctx->ns = N < DFM_KNN ? 0 : (N < DFM_KNN + DFM_NSAMPLE ? N - DFM_KNN : DFM_NSAMPLE);
   ctx->K = ctx->knn + ctx->ns;
   ctx->sym = sym;
+  // grow-only arena (4096 residues up front, doubling): the stream is only synchronised when a complex is larger than
+  // anything this context has seen -- never in a db5-sized sweep (largest complex 2548 residues)
   if ((size_t)N * H > ctx->h0_cap) {
+    size_t cap = ctx->h0_cap ? ctx->h0_cap : (size_t)4096 * H;
+    while (cap < (size_t)N * H) cap *= 2;
     CUDA_TRY(cudaStreamSynchronize(s));
     cudaFree(ctx->h0);
-    CUDA_TRY(cudaMalloc(&ctx->h0, sizeof(float) * (size_t)N * H));
-    ctx->h0_cap = (size_t)N * H;
+    ctx->h0 = nullptr; ctx->h0_cap = 0;
+    CUDA_TRY(cudaMalloc(&ctx->h0, sizeof(float) * cap));
+    ctx->h0_cap = cap;
   }
   if ((size_t)R * 9 > ctx->rec_cap) {
+    size_t cap = ctx->rec_cap ? ctx->rec_cap : (size_t)4096 * 9;
+    while (cap < (size_t)R * 9) cap *= 2;
     CUDA_TRY(cudaStreamSynchronize(s));
     cudaFree(ctx->rec_pos);
-    CUDA_TRY(cudaMalloc(&ctx->rec_pos, sizeof(float) * (size_t)R * 9));
-    ctx->rec_cap = (size_t)R * 9;
+    ctx->rec_pos = nullptr; ctx->rec_cap = 0;
+    CUDA_TRY(cudaMalloc(&ctx->rec_pos, sizeof(float) * cap));
+    ctx->rec_cap = cap;
   }
   CUDA_TRY(cudaMemcpyAsync(ctx->rec_pos, rec_pos, sizeof(float) * (size_t)R * 9, cudaMemcpyDeviceToDevice, s));
   int rc = launch_single_embed(ctx, rec_x, lig_x, s);
@@ -290,10 +304,6 @@ extern "C" int dfm_set_receptor_pose(dfm_ctx* ctx, const float* rec_pos, void* s
 }
 
 // ---------------------------------------------------------------------------------------------------
-static int linear(dfm_ctx* ctx, bool fp32, const LinearArgs& a, cudaStream_t s) {
-  return fp32 ? launch_linear_simt(ctx, a, s) : launch_linear_tc(ctx, a, s);
-}
-
 static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* t, const int32_t* edges,
                         const float* exp_noise, uint64_t seed, uint64_t stream_base, uint32_t fwd_index, uint32_t flags,
                         float* tr_score, float* rot_score, float* f, float* energy, int32_t* clashes, int32_t* edges_out,
@@ -309,10 +319,8 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
                                sizeof(int32_t) * ctx->K, (size_t)M, cudaMemcpyDeviceToDevice, s));
   }
   if ((rc = launch_broadcast_h0(ctx, B, ws, s))) return rc;
-  const bool fast = !fp32 && ctx->edge_kernel == 1;
-  for (int l = 0; fast && l < DFM_DEPTH; ++l) {
+  for (int l = 0; !fp32 && l < DFM_DEPTH; ++l) {
     // throughput path: fp16 activations between kernels, warp-specialised edge kernel, fused node-side GEMMs
-    const LayerW& w = ctx->layer[l];
     const bool last = l == DFM_DEPTH - 1;
     __half* Ah = reinterpret_cast<__half*>(ws.A);
     __half* Bm = reinterpret_cast<__half*>(ws.Bm);
@@ -321,7 +329,7 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
     ea.lig_only = last && !want_energy;   // the receptor rows' layer-5 messages only feed the node update the energy head needs
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
-    ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf; ea.coord_img = w.img_Wc1s;
+    ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
     const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
     if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
     if ((rc = launch_edge_ws(ctx, ea, ws.emeta, Ah, ws.agg16, s))) return rc;
@@ -335,54 +343,33 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     if ((rc = launch_graphnorm_stats(ctx, B, l, ws.z, ws.gscale, ws.gshift, s))) return rc;
     if ((rc = launch_node_h(ctx, l, M, ws.z, ws.gscale, ws.gshift, ws.h, ws.h16, s))) return rc;
   }
-  for (int l = 0; !fast && l < DFM_DEPTH; ++l) {
+  for (int l = 0; fp32 && l < DFM_DEPTH; ++l) {
+    // parity path (DFM_PRECISION_FP32): fp32 FFMA kernels of simt.cu, one Linear at a time
     const LayerW& w = ctx->layer[l];
     const bool last = l == DFM_DEPTH - 1;
-    const bool ews = false;
-    __half* Ahi = reinterpret_cast<__half*>(ws.A);
-    __half* Alo = Ahi + (size_t)M * H;
     LinearArgs la{};
     la.A = ws.h; la.a_scale = 1.f; la.M = M;
     // A = W1s h + b1
-    la.W32 = w.W1; la.ldw = 641; la.w_col0 = 0; la.Wimg = w.img_W1s; la.bias = w.b1eff; la.add = nullptr;
-    la.out = ws.A; la.out16 = nullptr;
-    if (ews) { la.out = nullptr; la.out16 = Ahi; la.out16_lo = Alo; la.out_scale = 0.5f; }
-    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    la.W32 = w.W1; la.ldw = 641; la.w_col0 = 0; la.bias = w.b1eff; la.add = nullptr; la.out = ws.A;
+    if ((rc = launch_linear_simt(ctx, la, s))) return rc;
     // Bm = W1d h
-    la.w_col0 = 256; la.Wimg = w.img_W1d; la.bias = nullptr; la.out16_lo = nullptr;
-    if (fp32) { la.out = ws.Bm; la.out16 = nullptr; } else { la.out = nullptr; la.out16 = reinterpret_cast<__half*>(ws.Bm); }
-    if ((rc = linear(ctx, fp32, la, s))) return rc;
-    la.out_scale = 0.f;
+    la.w_col0 = 256; la.bias = nullptr; la.out = ws.Bm;
+    if ((rc = launch_linear_simt(ctx, la, s))) return rc;
     EdgeArgs ea{};
     ea.B = B; ea.N = N; ea.R = ctx->R; ea.K = ctx->K; ea.layer = l; ea.last = last;
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
     ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
-    const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
-    if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
-    if (ews) ea.coord_img = w.img_Wc1s;
-    if (fp32) {
-      if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
-    } else {
-      if ((rc = launch_edge_tc(ctx, ea, s))) return rc;
-    }
-    if (prof) {
-      CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], s));
-      ctx->prof_used += 2;
-    }
-    if (!fp32 && last && (rc = launch_coord_tc(ctx, ea, s))) return rc;
+    if ((rc = launch_edge_simt(ctx, ea, s))) return rc;
     if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
     // z = W3h h + b3 + W3a agg
-    la.A = ws.h; la.a_scale = 1.f; la.W32 = w.W3; la.ldw = 512; la.w_col0 = 0; la.Wimg = w.img_W3h; la.bias = w.b3;
-    la.add = nullptr; la.out = ws.z; la.out16 = nullptr;
-    if ((rc = linear(ctx, fp32, la, s))) return rc;
-    la.A = ws.agg; la.a_scale = fp32 ? 1.f : AGG_SCALE; la.w_col0 = 256; la.Wimg = w.img_W3a; la.bias = nullptr;
-    la.add = ws.z;
-    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    la.A = ws.h; la.W32 = w.W3; la.ldw = 512; la.w_col0 = 0; la.bias = w.b3; la.add = nullptr; la.out = ws.z;
+    if ((rc = launch_linear_simt(ctx, la, s))) return rc;
+    la.A = ws.agg; la.w_col0 = 256; la.bias = nullptr; la.add = ws.z;
+    if ((rc = launch_linear_simt(ctx, la, s))) return rc;
     if ((rc = launch_graphnorm_silu(ctx, B, l, ws, s))) return rc;
     // h += W4 y + b4
-    la.A = ws.y; la.a_scale = 1.f; la.W32 = w.W4; la.ldw = 256; la.w_col0 = 0; la.Wimg = w.img_W4; la.bias = w.b4;
-    la.add = ws.h; la.out = ws.h;
-    if ((rc = linear(ctx, fp32, la, s))) return rc;
+    la.A = ws.y; la.W32 = w.W4; la.ldw = 256; la.w_col0 = 0; la.bias = w.b4; la.add = ws.h; la.out = ws.h;
+    if ((rc = launch_linear_simt(ctx, la, s))) return rc;
   }
   float* trs = tr_score ? tr_score : ws.tsc;
   float* rots = rot_score ? rot_score : ws.tsc + (size_t)B * 4;
@@ -438,15 +425,38 @@ extern "C" int dfm_randomize_pose(dfm_ctx* ctx, int B, const float* lig_pos0, co
                                (cudaStream_t)stream);
 }
 
-// host-side schedules, fp64 like the reference's numpy (so3_diffuser.py:210-227, r3_diffuser.py:20-24)
-static double so3_g(double t) {
-  const double lo = 0.1, hi = 1.5;
+// host-side schedules, fp64 like the reference's numpy (so3_diffuser.py:210-227, r3_diffuser.py:20-24); the sigmas are the
+// checkpoint's hyper_parameters.diffuser values (dfm_set_schedule; defaults = both shipped checkpoints)
+static double so3_g(const dfm_ctx* c, double t) {
+  const double lo = c->so3_min_sigma, hi = c->so3_max_sigma;
   const double sg = log(t * exp(hi) + (1 - t) * exp(lo));
   return sqrt(2 * (exp(hi) - exp(lo)) * sg / exp(sg));
 }
-static double r3_g(double t) {
-  const double lo = 0.1, hi = 30.0;
+static double r3_g(const dfm_ctx* c, double t) {
+  const double lo = c->r3_min_sigma, hi = c->r3_max_sigma;
   return lo * pow(hi / lo, t) * sqrt(2 * (log(hi) - log(lo)));
+}
+
+extern "C" int dfm_set_schedule(dfm_ctx* ctx, double so3_min_sigma, double so3_max_sigma, double r3_min_sigma,
+                                double r3_max_sigma) {
+  if (!ctx) { dfm_set_error("null ctx"); return DFM_EINVAL; }
+  if (!(so3_min_sigma > 0) || !(so3_max_sigma > so3_min_sigma) || !(r3_min_sigma > 0) || !(r3_max_sigma > r3_min_sigma)) {
+    dfm_set_error("dfm_set_schedule: need 0 < min_sigma < max_sigma for both diffusers");
+    return DFM_EINVAL;
+  }
+  ctx->so3_min_sigma = so3_min_sigma; ctx->so3_max_sigma = so3_max_sigma;
+  ctx->r3_min_sigma = r3_min_sigma; ctx->r3_max_sigma = r3_max_sigma;
+  return DFM_OK;
+}
+
+extern "C" int dfm_interface_logits(dfm_ctx* ctx, int B, float* ires, void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  int rc = check_ws(ctx, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (!ires) { dfm_set_error("dfm_interface_logits: null output"); return DFM_EINVAL; }
+  if (!ctx->ires_W1t) { dfm_set_error("dfm_interface_logits: the to_ires.* weights were not supplied"); return DFM_EMISSING; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return launch_ires(ctx, B * ctx->N, ws.h, ires, (cudaStream_t)stream);
 }
 
 __global__ void k_fill(float* p, float v, int n) {
@@ -487,8 +497,8 @@ extern "C" int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_st
     if (flags & DFM_NOISE_ANNEAL) ns_tr = ns_rot = ts[i];
     else if (last) ns_tr = ns_rot = 0.f;
     else { ns_tr = tr_noise_scale; ns_rot = rot_noise_scale; }
-    if ((rc = launch_reverse_step(ctx, B, lig_pos, rot_update, tr_update, trs, rots, (float)so3_g((double)ts[i]),
-                                  (float)r3_g((double)ts[i]), dt, ns_rot, ns_tr, nullptr, seed, stream_base, (uint32_t)i,
+    if ((rc = launch_reverse_step(ctx, B, lig_pos, rot_update, tr_update, trs, rots, (float)so3_g(ctx, (double)ts[i]),
+                                  (float)r3_g(ctx, (double)ts[i]), dt, ns_rot, ns_tr, nullptr, seed, stream_base, (uint32_t)i,
                                   flags, s))) return rc;
     if (last) {
       if ((rc = forward_impl(ctx, B, lig_pos, tbuf, nullptr, nullptr, seed, stream_base, (uint32_t)num_steps,

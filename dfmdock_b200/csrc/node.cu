@@ -21,7 +21,7 @@ int launch_image_pack(dfm_ctx* ctx, const float* W, int ldw, int col0, float sca
 
 // T_l[r][c] = sum_e W1e[c][e] * [Ws | Wp][e][r]   (SURVEY App. A.5), plus the radial column w1r.
 __global__ void k_pair_table(const float* __restrict__ W1, const float* __restrict__ Ws, const float* __restrict__ Wp,
-                             int P, float* __restrict__ T32, __half* __restrict__ T16, float* __restrict__ w1r) {
+                             int P, float* __restrict__ T32, float* __restrict__ w1r) {
   const int r = blockIdx.x, c = threadIdx.x;
   float acc = 0.f;
   for (int e = 0; e < ED; ++e) {
@@ -29,35 +29,31 @@ __global__ void k_pair_table(const float* __restrict__ W1, const float* __restri
     acc = fmaf(W1[(size_t)c * 641 + 513 + e], emb, acc);
   }
   T32[(size_t)r * H + c] = acc;
-  T16[(size_t)r * H + c] = __float2half_rn(acc);
   if (r == 0) w1r[c] = W1[(size_t)c * 641 + 512];
 }
-// Merged gather tables for the tensor-core edge kernel: one row per (dist bin, relpos bin) pair -- with the three
+// Merged gather tables for the tensor-core edge kernel (stored pre-halved, see common.cuh): one row per (dist bin, relpos bin) pair -- with the three
 // zero-angle rows folded in for pairs whose angle bins are all 0 (masked: dist >= 22 A or self) -- and one row per
 // (omega, theta, phi) bin triple.  Sums are formed in fp32 and rounded to fp16 once.
-__global__ void k_merge_tables(const float* __restrict__ T32, __half* __restrict__ Tdrp, __half* __restrict__ Totp,
-                               __half* __restrict__ Tdrph, __half* __restrict__ Totph) {
+__global__ void k_merge_tables(const float* __restrict__ T32, __half* __restrict__ Tdrph, __half* __restrict__ Totph) {
   const int row = blockIdx.x, c = threadIdx.x;
   if (row < 2 * 40 * 66) {
     const int z = row / (40 * 66), d = (row / 66) % 40, rp = row % 66;
     float v = T32[(size_t)d * H + c] + T32[(size_t)(NSPATIAL + rp) * H + c];
     if (z) v += T32[(size_t)40 * H + c] + T32[(size_t)64 * H + c] + T32[(size_t)88 * H + c];
-    Tdrp[(size_t)row * H + c] = __float2half_rn(v);
     Tdrph[(size_t)row * H + c] = __float2half_rn(0.5f * v);
   } else {
     const int q = row - 2 * 40 * 66;
     const int o = q / (24 * 12), t = (q / 12) % 24, ph = q % 12;
     const float v = T32[(size_t)(40 + o) * H + c] + T32[(size_t)(64 + t) * H + c] + T32[(size_t)(88 + ph) * H + c];
-    Totp[(size_t)q * H + c] = __float2half_rn(v);
     Totph[(size_t)q * H + c] = __float2half_rn(0.5f * v);
   }
 }
 int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s) {
   LayerW& w = ctx->layer[l];
   k_pair_table<<<NSPATIAL + ctx->P, 256, 0, s>>>(w.W1, ctx->w["spatial_embed.weight"].d,
-                                                ctx->w["positional_embed.weight"].d, ctx->P, w.T32, w.T16, w.w1r);
+                                                ctx->w["positional_embed.weight"].d, ctx->P, w.T32, w.w1r);
   LAUNCH_CHECK(ctx);
-  k_merge_tables<<<2 * 40 * 66 + 24 * 24 * 12, 256, 0, s>>>(w.T32, w.Tdrp16, w.Totp16, w.Tdrp16h, w.Totp16h);
+  k_merge_tables<<<2 * 40 * 66 + 24 * 24 * 12, 256, 0, s>>>(w.T32, w.Tdrp16h, w.Totp16h);
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -353,6 +349,54 @@ int launch_energy(dfm_ctx* ctx, int B, bool fp32_path, Workspace& ws, float* ene
                                                           ctx->e_ln_w, ctx->e_ln_b, ctx->e_w, ws.esum);
   LAUNCH_CHECK(ctx);
   k_energy_finish<<<B, 32, 0, s>>>(ctx->R, ws.esum, energy, clashes);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ---- interface-residue head ---------------------------------------------------------------------------
+// ires = W5 SiLU(W3 SiLU(W1 h + b1) + b3) + b5, to_ires = Linear(256,512) SiLU Linear(512,512) SiLU Linear(512,1)
+// (src/models/score_net_mlsb.py:296-302, applied at :383).  Never read at inference (inference_base.py:494-500), so it is
+// only computed on request (dfm_interface_logits): one CTA per residue, weights pre-transposed to [in, out] so that the
+// 512 threads of a CTA read consecutive addresses.
+__global__ void k_transpose(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) { const int r = i / cols, c = i % cols; Wt[(size_t)c * rows + r] = W[i]; }
+}
+int launch_transpose(dfm_ctx* ctx, const float* W, int rows, int cols, float* Wt, cudaStream_t s) {
+  k_transpose<<<(rows * cols + 255) / 256, 256, 0, s>>>(W, rows, cols, Wt);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+__global__ void __launch_bounds__(512) k_ires(const float* __restrict__ h, const float* __restrict__ W1t,
+                                              const float* __restrict__ b1, const float* __restrict__ W3t,
+                                              const float* __restrict__ b3, const float* __restrict__ w5,
+                                              const float* __restrict__ b5, float* __restrict__ out) {
+  __shared__ float x[512];
+  __shared__ float red[16];
+  const int o = threadIdx.x;
+  const size_t row = blockIdx.x;
+  if (o < H) x[o] = h[row * H + o];
+  __syncthreads();
+  float a = b1[o];
+  for (int k = 0; k < H; ++k) a = fmaf(x[k], W1t[(size_t)k * 512 + o], a);
+  a = silu_acc(a);
+  __syncthreads();
+  x[o] = a;
+  __syncthreads();
+  float c = b3[o];
+  for (int k = 0; k < 512; ++k) c = fmaf(x[k], W3t[(size_t)k * 512 + o], c);
+  float v = warp_sum(silu_acc(c) * w5[o]);
+  if ((o & 31) == 0) red[o >> 5] = v;
+  __syncthreads();
+  if (o < 16) {
+    v = red[o];
+#pragma unroll
+    for (int d = 8; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffu, v, d);
+    if (o == 0) out[row] = v + b5[0];
+  }
+}
+int launch_ires(dfm_ctx* ctx, int rows, const float* h, float* out, cudaStream_t s) {
+  k_ires<<<rows, 512, 0, s>>>(h, ctx->ires_W1t, ctx->ires_b1, ctx->ires_W3t, ctx->ires_b3, ctx->ires_w5, ctx->ires_b5, out);
   LAUNCH_CHECK(ctx);
   return 0;
 }

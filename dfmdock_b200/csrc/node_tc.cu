@@ -1,18 +1,14 @@
-// Node-side tcgen05 kernels of the throughput path (per-residue contractions with 256-wide operands, HBM-bound):
-//   MODE_AB  Ah = fp16((W1s h + b1)/2), Bm = fp16((W1d h)/2)   node halves of edge_mlp.0   (src/models/egnn.py:95-104)
-//   MODE_Z   z = W3h h + W3a agg + b3                           node_mlp.0 on [h, agg]      (src/models/egnn.py:106-116)
-//   MODE_H   h += W4 SiLU(GraphNorm(z)) + b4  (+ fp16 copy)     node_mlp.1-3 + residual     (src/models/egnn.py:74,106-116)
-//   MODE_C   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2), f_i = mean_k (x_i - x_j)/(|x_i - x_j| + 1) w   coord_model of the
-//            last layer, ligand rows only                                                   (src/models/egnn.py:118-148)
+// Coordinate head of the last E_GCL layer on the tensor cores (ligand rows only):
+//   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2),  f_i = mean_k (x_i - x_j) / (|x_i - x_j| + 1) w      (src/models/egnn.py:118-148)
+// m* = the gated messages edge_ws.cu spills for the ligand residues, [B*L, 64 slots, 256] fp16 (x 2^-6).
 //
 // One persistent CTA per SM, 19 warps:
-//   warps 0-15  workers: epilogue from TMEM (all modes); MODE_H also builds its operand (GraphNorm + SiLU of z) here
-//   warps 16-17 loaders: fp16 activations HBM -> shared memory with cp.async, straight into the K-major SWIZZLE_128B
+//   warps 0-15  workers: epilogue from TMEM (SiLU, dot with wc2, clamp, displacement, mean over the 60 slots)
+//   warps 16-17 loaders: the tile's K blocks HBM -> shared memory with cp.async, straight into the K-major SWIZZLE_128B
 //               operand layout, one 64-column K block (16 KB) at a time into a ring of four blocks
 //   warp  18    MMA issuer: one tcgen05.commit per K block (frees the ring slot) and one per tile (accumulator ready)
-// The 128 KB fp16 weight image is resident in shared memory.  MODE_Z contracts over K = 512 ([h | agg]) with the
-// output columns split over the two halves of the grid (N = 128 per CTA), so z is written once and no weight swap is
-// needed; the other modes use N = 256, K = 256.  Accumulators are double buffered in TMEM.
+// The 128 KB fp16 image of Wc1 (x 2^6) is resident in shared memory; accumulators are double buffered in TMEM.
+// (The other node-side contractions live in node_t.cu.)
 #include "common.cuh"
 
 namespace ntc {
@@ -96,28 +92,11 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2, MODE_C = 3 };
-
 struct Params {
   int M, ntiles, N;
-  // MODE_AB: X = h16; CTAs [0, grid/2) use W0/bias0/out0, the rest W1/(no bias)/out1; out = fp16(0.5 * (acc + bias))
-  // MODE_Z : K blocks 0-3 from X = h16, 4-7 from X2 = agg16; CTAs [0, grid/2) use W0 (output columns 0-127), the
-  //          rest W1 (columns 128-255); out32[:, half] = acc + bias0[half]
-  // MODE_H : operand = fp16(SiLU(z * gscale[b] + gshift[b])) with W0; h = h + acc + bias0; also h16
-  // MODE_C : X = gated messages of the ligand residues [B*L, 64, 256] fp16 (x 2^-6; W0 = Wc1 x 2^6), bias0 = bc1
-  const __half* X;
-  const __half* X2;
-  const __half* W0;
-  const __half* W1;
-  const float* bias0;
-  __half* out0;
-  __half* out1;
-  float* out32;
-  const float* z;
-  const float* gscale;   // [B, 256]
-  const float* gshift;   // [B, 256]
-  float* h;
-  __half* h16;
+  const __half* X;       // gated messages of the ligand residues [B*L, 64, 256] fp16 (x 2^-6)
+  const __half* W0;      // Wc1 x 2^6 image
+  const float* bias0;    // bc1
   const float* wc2;      // [256]
   const int32_t* nbr;    // [B*N, 64]
   const float* pos;      // [B*N, 3, 3] centred backbone
@@ -125,13 +104,11 @@ struct Params {
   int R, K;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
-  constexpr int KB = (MODE == MODE_Z) ? 8 : 4;            // K blocks per tile
-  constexpr int NCOL = (MODE == MODE_Z) ? 128 : 256;      // accumulator columns per tile
+__global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
+  constexpr int KB = 4;                                   // K blocks per tile
+  constexpr int NCOL = 256;                               // accumulator columns per tile
   constexpr uint32_t W_KBLK = NCOL * 128;                 // bytes per K block of the weight image
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr bool SPLIT = (MODE == MODE_AB || MODE == MODE_Z);   // the two halves of the grid use different weights
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -141,29 +118,21 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 32;
   const uint32_t bar_accf = sbase + OFF_BAR + 64, bar_acce = sbase + OFF_BAR + 80;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  const int half_grid = (int)gridDim.x >> 1;
-  const int side = (SPLIT && (int)blockIdx.x >= half_grid) ? 1 : 0;
-  const int cta = SPLIT ? ((int)blockIdx.x - side * half_grid) : (int)blockIdx.x;
-  const int ncta = SPLIT ? half_grid : (int)gridDim.x;
+  const int cta = (int)blockIdx.x, ncta = (int)gridDim.x;
 
   // ---- setup: weight image (four bulk copies, async proxy; only the MMA issuer waits for them), vectors, barriers, TMEM
   const uint32_t bar_w = sbase + OFF_BAR + 96;
-  {
-    if (tid < 256) {
-      float b = p.bias0 ? p.bias0[tid] : 0.f;
-      if (MODE == MODE_AB && side) b = 0.f;
-      vbias[tid] = b;
-      if (MODE == MODE_C) vbias[256 + tid] = p.wc2[tid];
-    }
+  if (tid < 256) {
+    vbias[tid] = p.bias0[tid];
+    vbias[256 + tid] = p.wc2[tid];
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(W_BYTES) : "memory");
-    const char* wsrc = reinterpret_cast<const char*>(side ? p.W1 : p.W0);
+    const char* wsrc = reinterpret_cast<const char*>(p.W0);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -210,85 +179,38 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
     __syncwarp();
   } else if (warp >= NWORK) {
     // =================================== LOADERS ======================================================
-    if (MODE != MODE_H) {
-      const int lw = warp - NWORK;                           // loader 0 takes even K blocks, loader 1 odd ones
-      const int c8 = lane & 7, rsub = lane >> 3;
-      uint32_t c = 0;
-      for (int tile = cta; tile < p.ntiles; tile += ncta) {
-        const int row0 = tile * TILE_M;
+    const int lw = warp - NWORK;                           // loader 0 takes even K blocks, loader 1 odd ones
+    const int c8 = lane & 7, rsub = lane >> 3;
+    uint32_t c = 0;
+    for (int tile = cta; tile < p.ntiles; tile += ncta) {
+      const int row0 = tile * TILE_M;
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb, ++c) {
-          if ((kb & 1) != lw) continue;
-          const uint32_t slot = c & 3u;
-          if (c >= 4) mbar_wait(bar_empty + 8 * slot, ((c >> 2) - 1) & 1u);
-          const __half* X = (MODE == MODE_Z && kb >= 4) ? p.X2 : p.X;
-          const int kcol = (kb & 3) * 64 + c8 * 8;
-          const uint32_t dst0 = sbase + OFF_S + slot * S_KBLK;
+      for (int kb = 0; kb < KB; ++kb, ++c) {
+        if ((kb & 1) != lw) continue;
+        const uint32_t slot = c & 3u;
+        if (c >= 4) mbar_wait(bar_empty + 8 * slot, ((c >> 2) - 1) & 1u);
+        const int kcol = kb * 64 + c8 * 8;
+        const uint32_t dst0 = sbase + OFF_S + slot * S_KBLK;
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int r = rsub + 4 * i;
-            const int m = row0 + r;
-            const bool ok = m < p.M;
-            cp_async16(dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4), X + (size_t)(ok ? m : 0) * H + kcol, ok ? 16u : 0u);
-          }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * slot) : "memory");
+        for (int i = 0; i < 32; ++i) {
+          const int r = rsub + 4 * i;
+          const int m = row0 + r;
+          // pad slots (K..63) are never written by the edge kernel: zero-fill them instead of reading stale memory
+          const bool ok = m < p.M && (r & 63) < p.K;
+          cp_async16(dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4), p.X + (size_t)(ok ? m : 0) * H + kcol, ok ? 16u : 0u);
         }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * slot) : "memory");
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
   } else {
     // =================================== WORKERS ======================================================
     const int q = warp & 3, cq = warp >> 2;                  // TMEM lane quarter / column quarter
     const int erow = q * 32 + lane;
-    constexpr int CW = NCOL / 4;                             // accumulator columns per thread (64 or 32)
-    uint32_t cb = 0;                                         // MODE_H: running K-block count of the builds
-
-    // MODE_H operand: y = SiLU(z * gscale[b] + gshift[b]) -> fp16, one K block (64 columns) at a time;
-    // 8 lanes per row (8 columns each), 4 rows per warp instruction, 8 rows per warp and K block
-    auto build_h = [&](int tile) {
-      const int c8 = lane & 7, rsub = lane >> 3;
-#pragma unroll 1
-      for (int kb = 0; kb < 4; ++kb, ++cb) {
-        const uint32_t slot = cb & 3u;
-        const int col = kb * 64 + c8 * 8;
-        float4 z0[2], z1[2];
-        int mrow[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int r = warp * 8 + 4 * i + rsub;
-          const int m = tile * TILE_M + r;
-          mrow[i] = m;
-          z0[i] = make_float4(0.f, 0.f, 0.f, 0.f); z1[i] = z0[i];
-          if (m < p.M) {
-            const float4* zp = reinterpret_cast<const float4*>(p.z + (size_t)m * H + col);
-            z0[i] = __ldg(zp); z1[i] = __ldg(zp + 1);
-          }
-        }
-        if (cb >= 4) mbar_wait(bar_empty + 8 * slot, ((cb >> 2) - 1) & 1u);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int r = warp * 8 + 4 * i + rsub;
-          float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (mrow[i] < p.M) {
-            const int b = mrow[i] / p.N;
-            const float4* sc = reinterpret_cast<const float4*>(p.gscale + (size_t)b * H + col);
-            const float4* sh = reinterpret_cast<const float4*>(p.gshift + (size_t)b * H + col);
-            const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
-            x[0] = silu_tanh(fmaf(z0[i].x, s0.x, h0.x)); x[1] = silu_tanh(fmaf(z0[i].y, s0.y, h0.y));
-            x[2] = silu_tanh(fmaf(z0[i].z, s0.z, h0.z)); x[3] = silu_tanh(fmaf(z0[i].w, s0.w, h0.w));
-            x[4] = silu_tanh(fmaf(z1[i].x, s1.x, h1.x)); x[5] = silu_tanh(fmaf(z1[i].y, s1.y, h1.y));
-            x[6] = silu_tanh(fmaf(z1[i].z, s1.z, h1.z)); x[7] = silu_tanh(fmaf(z1[i].w, s1.w, h1.w));
-          }
-          *reinterpret_cast<uint4*>(smem + OFF_S + slot * S_KBLK + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4)) = pack8(x);
-        }
-        fence_async_smem();
-        mbar_arrive(bar_full + 8 * slot);
-      }
-    };
+    constexpr int CW = NCOL / 4;                             // accumulator columns per thread (64)
 
     auto epilogue = [&](int tile, int buf) {
-      const int mrow = tile * TILE_M + erow;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NCOL + cq * CW);
       float dotp = 0.f;
 #pragma unroll
@@ -300,106 +222,56 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
           tc_fence_before();
           mbar_arrive(bar_acce + 8 * buf);
         }
-        const int col0 = cq * CW + c * 32;                         // column inside this CTA's accumulator
-        const int gcol0 = (MODE == MODE_Z ? side * 128 : 0) + col0; // column of the [M, 256] output
-        if (MODE == MODE_C) {
+        const int col0 = cq * CW + c * 32;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
-        } else if (mrow < p.M) {
-          const size_t o = (size_t)mrow * H + gcol0;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += vbias[gcol0 + e];
-          if (MODE == MODE_AB) {
-            __half* out = side ? p.out1 : p.out0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] *= 0.5f;
-#pragma unroll
-            for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(out + o + e8 * 8) = pack8(v + e8 * 8);
-          } else if (MODE == MODE_Z) {
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4)
-              *reinterpret_cast<float4*>(p.out32 + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 hv = *reinterpret_cast<const float4*>(p.h + o + e4 * 4);
-              v[e4 * 4] += hv.x; v[e4 * 4 + 1] += hv.y; v[e4 * 4 + 2] += hv.z; v[e4 * 4 + 3] += hv.w;
-              *reinterpret_cast<float4*>(p.h + o + e4 * 4) = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-            }
-#pragma unroll
-            for (int e8 = 0; e8 < 4; ++e8) *reinterpret_cast<uint4*>(p.h16 + o + e8 * 8) = pack8(v + e8 * 8);
-          }
-        }
+        for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
       }
-      if (MODE == MODE_C) {
-        // tile = 2 ligand residues x 64 slots: clamp(dot) -> displacement along x_i - x_j -> mean over the K slots
-        float* part = reinterpret_cast<float*>(smem + OFF_PART);
-        float* fpart = part + 512;
-        const int total = p.M / SLOTS;                       // B * L residues
-        const int node = tile * 2 + (erow >> 6), k = erow & 63;
-        const bool valid = node < total && k < p.K;
-        part[cq * 128 + erow] = dotp;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (cq == 0 && valid) {
-          const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
-          const int L = p.N - p.R;
-          const int b = node / L, i = p.R + node % L;
-          const size_t gi = (size_t)b * p.N + i;
-          const int j = __ldg(p.nbr + gi * SLOTS + k);
-          const float* pi = p.pos + gi * 9 + 3;
-          const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
-          const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
-          const float rad = dx * dx + dy * dy + dz * dz;
-          const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
-          fx = dx * sc; fy = dy * sc; fz = dz * sc;
-        }
-        if (cq == 0) {
-          fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-          if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid < 2) {
-          const int nd = tile * 2 + tid;
-          if (nd < total) {
-            const float inv = 1.f / (float)p.K;
-            float* fo = p.fbuf + (size_t)nd * 4;
-            fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
-            fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
-            fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
-            fo[3] = 0.f;
-          }
+      // tile = 2 ligand residues x 64 slots: clamp(dot) -> displacement along x_i - x_j -> mean over the K slots
+      float* part = reinterpret_cast<float*>(smem + OFF_PART);
+      float* fpart = part + 512;
+      const int total = p.M / SLOTS;                       // B * L residues
+      const int node = tile * 2 + (erow >> 6), k = erow & 63;
+      const bool valid = node < total && k < p.K;
+      part[cq * 128 + erow] = dotp;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      float fx = 0.f, fy = 0.f, fz = 0.f;
+      if (cq == 0 && valid) {
+        const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
+        const int L = p.N - p.R;
+        const int b = node / L, i = p.R + node % L;
+        const size_t gi = (size_t)b * p.N + i;
+        const int j = __ldg(p.nbr + gi * SLOTS + k);
+        const float* pi = p.pos + gi * 9 + 3;
+        const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
+        const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+        const float rad = dx * dx + dy * dy + dz * dz;
+        const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
+        fx = dx * sc; fy = dy * sc; fz = dz * sc;
+      }
+      if (cq == 0) {
+        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+        if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tid < 2) {
+        const int nd = tile * 2 + tid;
+        if (nd < total) {
+          const float inv = 1.f / (float)p.K;
+          float* fo = p.fbuf + (size_t)nd * 4;
+          fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
+          fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
+          fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
+          fo[3] = 0.f;
         }
       }
     };
 
     int it = 0;
-    if (MODE == MODE_H) {
-      // build(t) -> epilogue(t-1) -> build(t+1) ...: the MMA of tile t runs under the epilogue of tile t-1
-      int prev = -1;
-      for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
-        build_h(tile);
-        if (prev >= 0) {
-          const int pb = (it - 1) & 1;
-          mbar_wait(bar_accf + 8 * pb, (uint32_t)(((it - 1) >> 1) & 1));
-          tc_fence_after();
-          epilogue(prev, pb);
-        }
-        prev = tile;
-      }
-      if (prev >= 0) {
-        const int pb = (it - 1) & 1;
-        mbar_wait(bar_accf + 8 * pb, (uint32_t)(((it - 1) >> 1) & 1));
-        tc_fence_after();
-        epilogue(prev, pb);
-      }
-    } else {
-      for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
-        const int buf = it & 1;
-        mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
-        tc_fence_after();
-        epilogue(tile, buf);
-      }
+    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      epilogue(tile, buf);
     }
   }
   tc_fence_before();
@@ -409,14 +281,13 @@ __global__ void __launch_bounds__(NT, 1) k_node(const Params p) {
   }
 }
 
-template <int MODE>
 static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
   static unsigned long long attr_devices = 0;
   if (dfm_once_per_device(attr_devices, ctx->device)) {
-    CUDA_TRY(cudaFuncSetAttribute(k_node<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(k_coord, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
   }
   if (grid <= 0) return 0;
-  k_node<MODE><<<grid, NT, SMEM_ALLOC, s>>>(p);
+  k_coord<<<grid, NT, SMEM_ALLOC, s>>>(p);
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -439,15 +310,12 @@ int launch_image_pack_z(dfm_ctx* ctx, const float* W3, float scale_hi, __half* i
   return 0;
 }
 
-// MODE_AB / MODE_Z / MODE_H are launched from node_t.cu (transposed formulation, coalesced epilogue); this file's
-// instantiation that is used on the hot path is MODE_C.
-
-// per-residue force of the ligand (last layer): replaces tc.cu k_tc<COORD> on the throughput path
+// per-residue force of the ligand (last layer)
 int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   const LayerW& w = ctx->layer[a.layer];
   ntc::Params p{};
   const int L = a.N - a.R;
   p.M = a.B * L * SLOTS; p.ntiles = (a.B * L + 1) / 2; p.N = a.N; p.R = a.R; p.K = a.K;
   p.X = a.mstar; p.W0 = w.img_Wc1s; p.bias0 = w.bc1; p.wc2 = w.wc2; p.nbr = a.nbr; p.pos = a.pos; p.fbuf = a.fbuf;
-  return ntc::launch<ntc::MODE_C>(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
+  return ntc::launch(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
 }

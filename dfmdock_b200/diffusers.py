@@ -9,17 +9,24 @@ import numpy as np
 import torch
 
 
+def _reverse_increment(g_t, score_t, dt, noise_scale, ode):
+    """One Euler-Maruyama increment of the reverse VE-SDE  dx = g^2 score dt + g sqrt(dt) (noise_scale z),  z ~ N(0, I_3),
+    or of its probability-flow ODE  dx = g^2 score dt / 2  (no random draw).  g_t is the fp64 host scalar g(t)."""
+    g = float(g_t)
+    if ode:
+        return ((0.5 * (g * g)) * score_t * dt).float()
+    z = noise_scale * torch.randn(1, 3, device=score_t.device)
+    return ((g * g) * score_t * dt + (g * torch.sqrt(dt)) * z).float()
+
+
 class _ReverseMixin:
+    """torch_reverse(score_t, dt, t, noise_scale, ode) with the reference's argument order and RNG consumption
+    (src/utils/so3_diffuser.py:344-369, src/utils/r3_diffuser.py:40-55): t must be a Python / numpy scalar."""
+
     def torch_reverse(self, score_t, dt, t, noise_scale=1.0, ode=False):
         if not np.isscalar(t):
-            raise ValueError(f"{t} must be a scalar.")
-        g_t = self.diffusion_coef(t)
-        if not ode:
-            z = noise_scale * torch.randn(1, 3, device=score_t.device)
-            perturb = (g_t ** 2) * score_t * dt + g_t * torch.sqrt(dt) * z
-        else:
-            perturb = 0.5 * (g_t ** 2) * score_t * dt
-        return perturb.float()
+            raise ValueError("t must be a scalar, got %r" % (t,))
+        return _reverse_increment(self.diffusion_coef(t), score_t, torch.as_tensor(dt), noise_scale, ode)
 
 
 class SO3Diffuser(_ReverseMixin):

@@ -49,6 +49,15 @@ THREE = {"A": "ALA", "R": "ARG", "N": "ASN", "D": "ASP", "C": "CYS", "Q": "GLN",
          "Y": "TYR", "V": "VAL"}
 
 
+
+def complex_seed(seed, complex_id):
+    """Philox key of one complex: the run's seed mixed with a stable hash of the complex id, so that trajectory k of
+    different complexes does not reuse the same initial pose and noise (the reference advances ONE global RNG through
+    all complexes, src/inference_base.py:644-657); trajectory k of a complex is still Philox subsequence k."""
+    import zlib
+    return (int(seed) ^ (zlib.crc32(str(complex_id).encode()) << 20)) & 0xFFFFFFFFFFFFFFFF
+
+
 def set_seed(seed):
     """src/inference_base.py:24-32"""
     random.seed(seed)
@@ -174,7 +183,7 @@ def run(args, model, inputs, batch, device):
         model.set_complex(batch)
         res = model.sample(batch["lig_pos"], args.num_samples, num_steps=args.num_steps, tr_noise_scale=args.tr_noise_scale,
                            rot_noise_scale=args.rot_noise_scale, use_clash_force=args.use_clash_force,
-                           noise_annealing=args.noise_annealing, centre_mode=centre_mode, seed=args.seed, ode=ode, record=True)
+                           noise_annealing=args.noise_annealing, centre_mode=centre_mode, seed=complex_seed(args.seed, inputs["id"]), ode=ode, record=True)
         poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
                   int(res["num_clashes"][i])) for i in range(args.num_samples)]
         frames = [list(res["frames"][:, i].cpu()) for i in range(args.num_samples)]
@@ -182,7 +191,7 @@ def run(args, model, inputs, batch, device):
         res = sample_trajectories(model, batch, args.num_samples, num_steps=args.num_steps,
                                   use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing,
                                   tr_noise_scale=args.tr_noise_scale, rot_noise_scale=args.rot_noise_scale,
-                                  centre_mode=centre_mode, seed=args.seed, gather_poses=True, ode=ode)
+                                  centre_mode=centre_mode, seed=complex_seed(args.seed, inputs["id"]), gather_poses=True, ode=ode)
         poses = [(res["lig_pos"][i].cpu(), res["rot_update"][i].cpu(), res["tr_update"][i].cpu(), float(res["energy"][i]),
                   int(res["num_clashes"][i])) for i in range(args.num_samples)]
     return finish_samples(args, inputs, batch["rec_pos"], native_rec, native_lig, poses, frames, centre_mode, device)
@@ -232,7 +241,8 @@ def run_planned(args, model, paths_list, embedder, device):
     results, plan = sample_complex_set(
         model, [loader(c) for c in range(len(light))], sizes, args.num_samples, num_steps=args.num_steps,
         use_clash_force=args.use_clash_force, noise_annealing=args.noise_annealing, tr_noise_scale=args.tr_noise_scale,
-        rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode, seed=args.seed, ode=bool(getattr(args, "ode", False)))
+        rot_noise_scale=args.rot_noise_scale, centre_mode=centre_mode, seed=args.seed, ode=bool(getattr(args, "ode", False)),
+        seeds=[complex_seed(args.seed, id) for id, _, _ in paths_list])
     rows = []
     if _rank() == 0:
         for c, res in enumerate(results):

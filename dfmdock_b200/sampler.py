@@ -52,9 +52,10 @@ def Euler_Maruyama_sampler(model, batch, num_steps=40, device="cpu", batch_size=
                 ns_tr = ns_rot = 0.0
             else:
                 ns_tr, ns_rot = tr_noise_scale, rot_noise_scale
-            z = torch.cat([torch.randn(1, 3, device=dev), torch.randn(1, 3, device=dev)], dim=0)   # rot, then tr
+            # torch_reverse draws randn(1,3) only on the SDE branch (so3_diffuser.py:362-367): the ODE branch consumes no RNG
+            z = None if ode else torch.cat([torch.randn(1, 3, device=dev), torch.randn(1, 3, device=dev)], dim=0)[None]   # rot, then tr
             model.reverse_step(lig_pos, rot_update, tr_update, output["tr_score"], output["rot_score"], t_host, dt_host,
-                               ns_rot, ns_tr, z=z[None], use_clash_force=use_clash_force, centre_mode=centre_mode, ode=ode)
+                               ns_rot, ns_tr, z=z, use_clash_force=use_clash_force, centre_mode=centre_mode, ode=ode)
             if trajectory is not None:
                 trajectory.append(lig_pos[0].clone())
             if is_last:
@@ -99,19 +100,20 @@ def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_c
     out = {"rot_update": full[:, 0:3], "tr_update": full[:, 3:6], "energy": full[:, 6],
            "num_clashes": full[:, 7].round().long(), "lig_pos_local": local["lig_pos"], "local_range": (lo, hi)}
     if gather_poses:
-        out["lig_pos"] = dist_utils.gather_rows(local["lig_pos"].reshape(hi - lo, -1), num_samples, group).view(-1, L, 3, 3)
+        out["lig_pos"] = dist_utils.gather_rows(local["lig_pos"].reshape(hi - lo, L * 9), num_samples, group).view(-1, L, 3, 3)
     out["best"] = int(torch.argmin(out["energy"]).item()) if num_samples > 0 else -1
     return out
 
 
 def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-3, use_clash_force=False,
                        noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, seed=0, ode=False,
-                       group=None, min_nodes=8192):
+                       group=None, min_nodes=8192, seeds=None):
     """Many complexes x num_samples trajectories each (BASELINE config #5) over the ranks of `group`.
 
     loaders[c]() -> batch dict of complex c (called only on the ranks that own a chunk of it); sizes[c] = residues of
     complex c (for the plan, dfmdock_b200.distributed.plan_work).  Trajectory k of every complex uses Philox subsequence
-    k whatever the plan, so the result does not depend on the number of ranks.  One collective at the end: the chunks'
+    k whatever the plan, so the result does not depend on the number of ranks; seeds[c] (default: `seed` for all) is the
+    Philox key of complex c -- pass distinct values so that complexes do not share initial poses and noise.  One collective at the end: the chunks'
     result rows (pose, rot_update, tr_update, energy, num_clashes) are all-gathered as objects.
     Returns (results, plan): results[c] = dict of CPU tensors {lig_pos [T,L,3,3], rot_update [T,3], tr_update [T,3],
     energy [T], num_clashes [T], best} on every rank.
@@ -129,7 +131,8 @@ def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-
         for lo, hi in mine[c]:
             res = model.sample(batch["lig_pos"], hi - lo, num_steps=num_steps, eps=eps, tr_noise_scale=tr_noise_scale,
                                rot_noise_scale=rot_noise_scale, use_clash_force=use_clash_force,
-                               noise_annealing=noise_annealing, centre_mode=centre_mode, seed=seed, stream_base=lo, ode=ode)
+                               noise_annealing=noise_annealing, centre_mode=centre_mode,
+                               seed=seed if seeds is None else seeds[c], stream_base=lo, ode=ode)
             done.append((c, lo, hi, {k: v.cpu() for k, v in res.items()}))
     everything = [item for part in dist_utils.gather_objects(done, group) for item in part]
     results = []

@@ -19,12 +19,31 @@ from . import _lib
 from .checkpoint import load_checkpoint
 from .diffusers import R3Diffuser, SO3Diffuser
 
-HOT_PREFIXES = ("single_embed", "spatial_embed", "positional_embed", "network.", "to_energy", "t_embed", "tr_scale",
-                "rot_scale")
+HOT_PREFIXES = ("single_embed", "spatial_embed", "positional_embed", "network.", "to_energy", "to_ires", "t_embed",
+                "tr_scale", "rot_scale")
+
+# hyper_parameters.model values the kernels are built for (configs/model/score_model_mlsb.yaml; both shipped checkpoints)
+SUPPORTED_MODEL_HPARAMS = {"node_dim": 256, "edge_dim": 128, "inner_dim": 128, "depth": 6, "spatial_embed_dim": 100,
+                           "normalize": True}
+
+
+def validate_hparams(hparams):
+    """The CUDA kernels hard-wire the shipped architecture: 6 E_GCL layers, 256 / 128 / 128 widths, normalised coordinate
+    differences (egnn.py:144-146) and GraphNorm.  A checkpoint trained with anything else would load (same tensor shapes
+    for e.g. normalize=False) and give silently different scores -- refuse it instead."""
+    model = hparams.get("model", {}) if hasattr(hparams, "get") else {}
+    for key, want in SUPPORTED_MODEL_HPARAMS.items():
+        if key in model and model[key] != want:
+            raise ValueError("dfmdock_b200: hyper_parameters.model.%s = %r is not supported (the kernels are built for %r)"
+                             % (key, model[key], want))
+    so3 = hparams.get("diffuser", {}).get("so3", {}) if hasattr(hparams, "get") else {}
+    if so3.get("schedule", "logarithmic") != "logarithmic":
+        raise ValueError("dfmdock_b200: only the logarithmic SO(3) schedule is supported, got %r" % (so3.get("schedule"),))
 
 
 class Score_Model:
     def __init__(self, state_dict, hparams, precision="fp16"):
+        validate_hparams(hparams)
         self.hparams = hparams
         self.state_dict_cpu = {k: v.detach().float().contiguous() for k, v in state_dict.items()}
         self.so3_diffuser = SO3Diffuser(hparams["diffuser"]["so3"])
@@ -83,6 +102,9 @@ class Score_Model:
                 shape = (c_int64 * max(d.dim(), 1))(*d.shape)
                 _lib.check(lib.dfm_set_weight(ctx, name.encode(), _lib.ptr(d), shape, d.dim()), "dfm_set_weight(%s)" % name)
             _lib.check(lib.dfm_finalize_weights(ctx, self.cut_off, self._stream()), "dfm_finalize_weights")
+        # dfm_sample computes g(t) on the host from the checkpoint's own sigmas (hyper_parameters.diffuser)
+        _lib.check(lib.dfm_set_schedule(ctx, float(self.so3_diffuser.min_sigma), float(self.so3_diffuser.max_sigma),
+                                        float(self.r3_diffuser.min_sigma), float(self.r3_diffuser.max_sigma)), "dfm_set_schedule")
         return self
 
     def cuda(self, index=None):
@@ -207,6 +229,16 @@ class Score_Model:
                 forward_index, self._flags(want_energy, precision), _lib.ptr(out["tr_score"]), _lib.ptr(out["rot_score"]),
                 _lib.ptr(out["f"]), _lib.ptr(out.get("energy")), _lib.ptr(out.get("num_clashes")), _lib.ptr(out.get("edges")),
                 ws, nws, self._stream()), "dfm_score_forward")
+        return out
+
+    def interface_logits(self, B):
+        """ires = to_ires(h) [B, N] of the last score(..., want_energy=True) call with the same B (score_net_mlsb.py:383)."""
+        self._need_ctx()
+        R, L = self._complex
+        out = torch.empty(B, R + L, device=self.device)
+        ws, nws = self._workspace(B)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfm_interface_logits(self._ctx, B, _lib.ptr(out), ws, nws, self._stream()), "dfm_interface_logits")
         return out
 
     def debug_read(self, B, which, shape, dtype=torch.float32):
@@ -359,8 +391,10 @@ class Score_Model:
             "energy": o["energy"][0],
             "f": o["f"][0],
             "num_clashes": o["num_clashes"][0].long(),
-            # to_ires is never read at inference (inference_base.py:494-500); not computed, NaN so misuse is visible
-            "ires": torch.full((N, 1), float("nan"), device=self.device),
+            # to_ires (score_net_mlsb.py:383): never read at inference (inference_base.py:494-500), computed here only so
+            # that the returned dict is the reference's; checkpoints stripped of to_ires.* get NaN so misuse is visible
+            "ires": (self.interface_logits(1).view(N, 1) if "to_ires.0.weight" in self.state_dict_cpu
+                     else torch.full((N, 1), float("nan"), device=self.device)),
         }
 
     __call__ = forward

@@ -15,8 +15,10 @@
  *     allocates nothing in dfm_score_forward / dfm_reverse_step / dfm_sample (the workspace is
  *     handed in by the caller, sized by dfm_workspace_bytes).
  *   - all work is stream-ordered on the cudaStream_t passed as `stream` (a void* here so that the
- *     header needs no CUDA include); no entry point synchronises the device except dfm_create,
- *     dfm_finalize_weights and dfm_destroy.
+ *     header needs no CUDA include).  Entry points that synchronise: dfm_create, dfm_finalize_weights,
+ *     dfm_destroy (device / stream), dfm_profile_read (its own events), and dfm_set_complex ONLY when the
+ *     complex is larger than the context's grow-only arena (4096 residues up front, doubled on demand):
+ *     then it synchronises `stream` once and re-allocates.  Nothing else synchronises or allocates.
  *   - one context per (device, stream); contexts are independent; a context is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device every entry point fails with DFM_ECUDA.
  */
@@ -86,6 +88,10 @@ int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream);
 int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const float* rec_x, const float* lig_x,
                     const float* rec_pos, float sym, void* stream);
 
+/* Replaces: the sigmas SO3Diffuser / R3Diffuser take from hyper_parameters.diffuser (src/utils/so3_diffuser.py:22-31,
+ * src/utils/r3_diffuser.py:9-18), used by dfm_sample for g(t).  Defaults 0.1 / 1.5 / 0.1 / 30.0 (both shipped checkpoints). */
+int dfm_set_schedule(dfm_ctx* ctx, double so3_min_sigma, double so3_max_sigma, double r3_min_sigma, double r3_max_sigma);
+
 /* Replaces only the receptor backbone [R,3,3] of the current complex (the reference sampler re-sends
  * batch["rec_pos"] every step, inference_base.py:422); R must equal the current complex's. */
 int dfm_set_receptor_pose(dfm_ctx* ctx, const float* rec_pos, void* stream);
@@ -141,6 +147,12 @@ int dfm_sample(dfm_ctx* ctx, int B, const float* lig_pos0, int num_steps, float 
                float rot_noise_scale, uint32_t flags, uint64_t seed, uint64_t stream_base, float* lig_pos,
                float* rot_update, float* tr_update, float* energy, int32_t* num_clashes, void* workspace,
                size_t workspace_bytes, void* stream);
+
+/* Replaces: ires = to_ires(h) (src/models/score_net_mlsb.py:296-302, :383), the sixth entry of the reference's output
+ * dict.  Nothing reads it at inference (inference_base.py:494-500), so it is computed on request only: call after a
+ * dfm_score_forward with DFM_WANT_ENERGY (which runs the last node update) on the same B / workspace.  ires [B, N].
+ * Needs the to_ires.* tensors (dfm_set_weight); DFM_EMISSING otherwise. */
+int dfm_interface_logits(dfm_ctx* ctx, int B, float* ires, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels the library launched on behalf of this context since creation (bench.py "gpu_launches"). */
 uint64_t dfm_launch_count(const dfm_ctx* ctx);

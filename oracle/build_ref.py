@@ -38,17 +38,33 @@ def main(quiet=False, force=False):
     for cid in COMPLEXES:
         recs[cid] = load_db5_record(os.path.join(root, "data", "db5_test", cid + ".pt"))
         torch.save(recs[cid], os.path.join(OUT, "db5_%s.pt" % cid))
-    # goldens from the live reference: real checkpoints x real complexes, graph captured and stored
+    # goldens from the live reference: real checkpoints x real complexes, graph captured and stored.  Two kinds of pose:
+    #   "native": the bound pose of the record at t = 0.9 / 0.1
+    #   "far":    a randomize_pose start (inference_base.py:318-340: random rotation, translation ~ N(0, 30^2) per axis,
+    #             rescaled to a centroid separation drawn from 50..150 A), t = 1.0 -- what every trajectory begins from;
+    #             radial = |x_i - x_j|^2 reaches 1e4..1e5 A^2 there
+    # Seeds are fixed integers so that the file is reproducible.
     golden = []
     ref_shims.install()
     import models.score_net_mlsb as snm
-    for ck_name, path in ck.items():
+    from oracle import dfmdock_oracle as orc
+    from scipy.spatial.transform import Rotation
+    for ci, (ck_name, path) in enumerate(ck.items()):
         model, hp = ref_shims.build_reference_model(path)
         width = hp.model["positional_embed_dim"]
-        for cid in COMPLEXES:
-            batch = batch_from_record(recs[cid], pos_width=width)
-            for t in (0.9, 0.1):
+        for xi, cid in enumerate(COMPLEXES):
+            base = batch_from_record(recs[cid], pos_width=width)
+            cases = [("native", 0.9, None), ("native", 0.1, None), ("far", 1.0, 60.0), ("far", 1.0, 140.0)]
+            for ki, (pose, t, sep) in enumerate(cases):
+                seed = 1000 + 100 * ci + 10 * xi + ki
+                batch = dict(base)
                 batch["t"] = torch.tensor([t])
+                if pose == "far":
+                    g = torch.Generator().manual_seed(seed)
+                    rot0 = torch.from_numpy(Rotation.random(random_state=seed).as_matrix()).float()
+                    tr0 = torch.randn(1, 3, generator=g)
+                    tr0 = tr0 / tr0.norm() * sep          # separation of the CA centroids after randomize_pose
+                    batch["lig_pos"], _, _ = orc.randomize_pose(base["rec_pos"], base["lig_pos"], rot0, tr0)
                 captured = {}
                 orig = snm.get_knn_and_sample
 
@@ -59,17 +75,18 @@ def main(quiet=False, force=False):
 
                 snm.get_knn_and_sample = gk
                 try:
-                    torch.manual_seed(hash((ck_name, cid)) % 1000)
+                    torch.manual_seed(seed)
                     with torch.no_grad():
                         out = model(batch)
                 finally:
                     snm.get_knn_and_sample = orig
-                golden.append({"ckpt": ck_name, "complex": cid, "t": t, "nbr": captured["nbr"].to(torch.int16),
+                golden.append({"ckpt": ck_name, "complex": cid, "t": t, "pose": pose, "sep": sep, "seed": seed,
+                               "lig_pos": batch["lig_pos"].clone(), "nbr": captured["nbr"].to(torch.int16),
                                "tr_score": out["tr_score"], "rot_score": out["rot_score"], "energy": out["energy"],
                                "f": out["f"], "num_clashes": out["num_clashes"]})
     torch.save(golden, done)
     if not quiet:
-        print("wrote", OUT, [(g["ckpt"], g["complex"], g["t"], float(g["energy"])) for g in golden])
+        print("wrote", OUT, [(g["ckpt"], g["complex"], g["pose"], g["t"], float(g["energy"])) for g in golden])
 
 
 def extract_all_db5(quiet=False):

@@ -2,7 +2,8 @@
 
 Tolerances (stated per mode):
   fp32  (DFM_PRECISION_FP32, FFMA kernels):            5e-4 relative (L2) on f / scores / h, 2e-3 absolute on energy
-  fp16  (default: fp16 tcgen05 operands, fp32 accum):  2e-2 relative (L2) on f / scores / h, 5e-2 absolute on energy
+  fp16  (default: fp16 tcgen05 operands + fp16 SIMT, fp32 MMA accumulate):  1e-2 relative (L2) on f / scores / h (SURVEY 8c's
+        bound for the reduced-precision mode; measured worst 4.7e-3), 5e-2 absolute on energy
   integer outputs (bins, num_clashes, neighbour sets with injected noise): exact, except pair-feature bins whose
   angle lies within 1e-3 degree of a bin edge (libm vs CUDA atan2/acos): at most 0.05% of the bins may differ.
 """
@@ -13,7 +14,7 @@ from util import FWD_CASES, case_small, load_golden, max_abs, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(rel=5e-4, energy=2e-3), "fp16": dict(rel=2e-2, energy=5e-2)}
+TOL = {"fp32": dict(rel=5e-4, energy=2e-3), "fp16": dict(rel=1e-2, energy=5e-2)}
 
 
 def _model(sd, hp, precision):
@@ -246,7 +247,7 @@ def test_fp16_tensor_core_path_tracks_fp32_path():
         o = model.score(batch["lig_pos"][None], torch.tensor([item["t"]]), edges=item["nbr"][None].int(), want_energy=True)
         outs[precision] = {k: v.cpu().clone() for k, v in o.items()}
     for k in ("f", "tr_score", "rot_score"):
-        assert rel_err(outs["fp16"][k], outs["fp32"][k]) <= 2e-2, k
+        assert rel_err(outs["fp16"][k], outs["fp32"][k]) <= 1e-2, k
 
 
 @pytest.mark.parametrize("name,centre_mode", [("sampler_base_n70.pt", 0), ("sampler_near_n70.pt", 0), ("sampler_clash_n70.pt", 1)])
@@ -411,6 +412,8 @@ def test_real_checkpoints_real_complexes_vs_live_reference_golden(precision):
     models = {}
     worst = {}
     for g in golden:
+        if g.get("pose", "native") != "native":
+            continue                      # the far-pose cases are tests/test_gpu_configs.py's
         if g["ckpt"] not in models:
             ck = torch.load(os.path.join(REAL, g["ckpt"] + ".pt"), weights_only=False)
             models[g["ckpt"]] = Score_Model(ck["state_dict"], ck["hparams"], precision=precision).to("cuda")
@@ -418,7 +421,7 @@ def test_real_checkpoints_real_complexes_vs_live_reference_golden(precision):
         rec = torch.load(os.path.join(REAL, "db5_%s.pt" % g["complex"]), weights_only=False)
         batch = batch_from_record(rec, pos_width=model.pos_width)
         model.set_complex(batch)
-        out = model.score(batch["lig_pos"][None], torch.tensor([g["t"]]), edges=g["nbr"][None].int(), want_energy=True)
+        out = model.score(g.get("lig_pos", batch["lig_pos"])[None], torch.tensor([g["t"]]), edges=g["nbr"][None].int(), want_energy=True)
         for k in ("f", "tr_score", "rot_score"):
             e = rel_err(out[k].cpu()[0], g[k].reshape(out[k].shape[1:]))
             worst[k] = max(worst.get(k, 0.0), e)
@@ -481,7 +484,7 @@ STAT_CASES = {
 def test_free_running_sampler_matches_reference_distribution(case):
     """T5: 256 free-running trajectories of the batched Philox sampler (tensor-core path) against 64-96
     trajectories of the UNMODIFIED reference sampler on 1QA9 with a real checkpoint (tests/golden/make_stat_golden.py).
-    Two-sample Kolmogorov-Smirnov on final energy, ligand RMSD, |tr_update| and |rot_update|: p > 1e-3 each
+    Two-sample Kolmogorov-Smirnov on final energy, ligand RMSD, |tr_update| and |rot_update|: p > 0.01 each
     (a wrong schedule, noise scale, centre convention, clash force or score sign shifts these distributions by many sigma)."""
     import os
     from scipy.stats import ks_2samp
@@ -510,4 +513,4 @@ def test_free_running_sampler_matches_reference_distribution(case):
         report[k] = (float(st.statistic), float(st.pvalue), float(v.mean()), float(g[k].double().mean()))
     print("KS %s (statistic, p, mean cuda, mean reference):" % case, report)
     for k, (stat, pval, _, _) in report.items():
-        assert pval > 1e-3, (k, report)
+        assert pval > 0.01, (k, report)

@@ -248,3 +248,65 @@ def test_complex_set_sharding_over_gloo(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+_GLOO_FEW_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DFM_ROOT"])
+from dfmdock_b200 import sampler
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["DFM_PORT"], rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+
+class FakeModel:                        # stands in for the CUDA model: result rows encode the trajectory index
+    device = torch.device("cpu")
+    def set_complex(self, batch): pass
+    def sample(self, lig_pos0, n, stream_base=0, **kw):
+        k = torch.arange(stream_base, stream_base + n, dtype=torch.float32)
+        return {"lig_pos": k[:, None, None, None].expand(n, 5, 3, 3).clone(), "rot_update": k[:, None].expand(n, 3).clone(),
+                "tr_update": k[:, None].expand(n, 3).clone(), "energy": -k, "num_clashes": torch.zeros(n, dtype=torch.int32)}
+
+batch = {"lig_pos": torch.zeros(5, 3, 3)}
+# the CLI default: --num_samples 1 under a 2-rank torchrun -> rank 1's shard is EMPTY; both collectives must still complete
+for total in (1, 3):
+    out = sampler.sample_trajectories(FakeModel(), batch, total, num_steps=2, gather_poses=True)
+    assert out["lig_pos"].shape == (total, 5, 3, 3), out["lig_pos"].shape
+    assert torch.equal(out["lig_pos"][:, 0, 0, 0], torch.arange(total, dtype=torch.float32))
+    assert out["energy"].shape == (total,) and out["best"] == total - 1
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_fewer_trajectories_than_ranks_over_gloo(tmp_path):
+    """ADVICE r1: sample_trajectories(gather_poses=True) with an empty local shard (num_samples < world size)."""
+    script = tmp_path / "worker_few.py"
+    script.write_text(_GLOO_FEW_WORKER)
+    port = str(33500 + os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), DFM_ROOT=ROOT, DFM_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_unsupported_hparams_are_refused_and_complex_seeds_differ():
+    from dfmdock_b200 import Score_Model
+    from dfmdock_b200.inference import complex_seed
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd = synthetic_state_dict(0)
+    for key, bad in (("normalize", False), ("depth", 7), ("node_dim", 128), ("inner_dim", 64)):
+        hp = synthetic_hparams()
+        hp["model"][key] = bad
+        with pytest.raises(ValueError, match=key):
+            Score_Model(sd, hp)
+    hp = synthetic_hparams()
+    hp["diffuser"]["so3"]["schedule"] = "linear"
+    with pytest.raises(ValueError):
+        Score_Model(sd, hp)
+    # trajectory k of different complexes must not share a Philox key; the same (seed, id) must always give the same key
+    seeds = {complex_seed(42, cid) for cid in ("1QA9", "7CEI", "4POU", "1N2C")}
+    assert len(seeds) == 4 and complex_seed(42, "1QA9") == complex_seed(42, "1QA9") != complex_seed(43, "1QA9")
+    assert all(0 <= s < 2 ** 64 for s in seeds)
