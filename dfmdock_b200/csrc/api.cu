@@ -21,6 +21,11 @@ void dfm_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* dfm_last_error(void) { return g_err; }
+bool dfm_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DFM_PDL"); on = e ? (atoi(e) != 0) : 1; }
+  return on != 0;
+}
 extern "C" const char* dfm_version(void) { return "dfmdock_b200 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -200,7 +205,7 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
     if ((rc = launch_image_pack(ctx, w.W4, 256, 0, 1.f, w.img_W4, s))) return rc;
     if ((rc = launch_image_pack(ctx, w.W2, 256, 0, 0.5f, w.img_W2h, s))) return rc;
     if ((rc = launch_image_pack_z(ctx, w.W3, AGG_UNSCALE, w.img_W3z0, w.img_W3z1, s))) return rc;
-    if (w.Wc1 && (rc = launch_image_pack(ctx, w.Wc1, 256, 0, 64.f, w.img_Wc1s, s))) return rc;
+    if (w.Wc1 && (rc = launch_image_pack_perm(ctx, w.Wc1, 256, 64.f, w.img_Wc1s, s))) return rc;
   }
   NEED("to_energy.0.weight", {H, 2 * H}); ctx->We = tmp;
   NEED("to_energy.1.weight", {H}); ctx->e_ln_w = tmp;

@@ -6,6 +6,7 @@
 
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dfmdock_b200.h"
@@ -51,6 +52,29 @@ __host__ inline bool dfm_once_per_device(unsigned long long& mask, int device) {
     }                                                                                       \
   } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched through dfm_launch_pdl may be scheduled while its predecessor in the
+// stream is still draining, runs its prologue (barrier init, TMEM allocation, the bulk copy of its constant weight image)
+// and blocks in pdl_wait() until the predecessor has completed and its writes are visible; pdl_trigger() at the top of a
+// kernel allows ITS successor to be scheduled as soon as SM resources free up.  Every kernel on the chain executes
+// pdl_wait() before it touches anything a predecessor wrote (or still reads), so completion order stays the stream order.
+// Without the launch attribute both instructions are no-ops.  DFM_PDL=0 in the environment disables the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool dfm_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t dfm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = dfm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 struct WTensor {
   float* d = nullptr;
   std::vector<int64_t> shape;
@@ -86,7 +110,7 @@ struct LayerW {
   __half* Tdrp16h;      // [(z*40+d)*66+rp][256] merged dist + relpos rows (z=1: + the three zero-angle rows) / 2, fp16 of the fp32 sum
   __half* Totp16h;      // [(o*24+t)*12+p][256] merged omega + theta + phi rows / 2
   __half* img_W2h;      // W2 / 2
-  __half* img_Wc1s;     // Wc1 x 2^6 (gated messages are spilled x 2^-6)
+  __half* img_Wc1s;     // Wc1 x 2^6 (gated messages are spilled x 2^-6), K in the spill's fragment order (node_tc.cu)
   __half* img_W3z0;     // [W3h | W3a x 2^6] rows 0-127, K = 512 (node_tc.cu MODE_Z)
   __half* img_W3z1;     // rows 128-255
 };
@@ -216,6 +240,7 @@ int launch_force_head(dfm_ctx* ctx, int B, const float* t, Workspace& ws, float*
 int launch_energy(dfm_ctx* ctx, int B, bool fp32_path, Workspace& ws, float* energy, int32_t* clashes,
                   cudaStream_t s);
 int launch_image_pack(dfm_ctx* ctx, const float* W, int ldw, int col0, float scale, __half* img, cudaStream_t s);
+int launch_image_pack_perm(dfm_ctx* ctx, const float* W, int ldw, float scale, __half* img, cudaStream_t s);
 int launch_pair_table(dfm_ctx* ctx, int l, cudaStream_t s);
 int launch_single_embed(dfm_ctx* ctx, const float* rec_x, const float* lig_x, cudaStream_t s);
 int launch_transpose(dfm_ctx* ctx, const float* W, int rows, int cols, float* Wt, cudaStream_t s);

@@ -106,6 +106,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_BULK_W
 #define EWS_BULK_W 1      // weight image by cp.async.bulk (TMA 1-D), overlapped with the rest of the set-up and the first tile's build
 #endif
+#ifndef EWS_SKIP_PAD
+#define EWS_SKIP_PAD 1    // a producer warp whose second 4-row group lies entirely in the pad slots K..63 (warps 7 and 15 at K = 60)
+#endif                    // skips it; those rows keep the raw B_j the loaders staged (finite; their gate is 0)
 #ifndef EWS_FOLD
 #define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
 #endif
@@ -262,6 +265,9 @@ __device__ __forceinline__ void lane_group_sum_h2(uint32_t* v, int lane) {
   }
 }
 
+// LAST: the last E_GCL layer (spill of the ligand rows' gated messages for the coordinate head, optional ligand-only tile walk);
+// a separate instantiation so that the five other launches carry neither its code nor its registers
+template <bool LAST>
 __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -275,8 +281,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   const uint32_t bar_acce = sbase + OFF_BAR + 80;       // [2]
   const uint32_t bar_w = sbase + OFF_BAR + 128;         // weight image landed (bulk copy)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();            // the next kernel of the stream may start its prologue while this one drains (common.cuh)
 
-  // ---- one-time setup ------------------------------------------------------------------------------
+  // ---- one-time setup (constants only: nothing a predecessor kernel wrote is read before pdl_wait) -----
   {
 #if !EWS_BULK_W
     const uint4* src = reinterpret_cast<const uint4*>(p.Wimg);
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // Ah / Bm / emeta of the preceding kernels are complete and visible from here on
   // contiguous tile ranges: concurrently running CTAs work on different trajectories, so the gathered B_j rows are
   // not hot lines shared by all SMs (strided assignment had every SM hammer the same 300 rows at the same time)
   const int t_begin = (int)blockIdx.x * p.chunk;
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   // logical tile index -> tile of the [B*N/2] node-pair grid.  Ligand-only launches walk, per trajectory, the tiles
   // (b N + R) / 2 .. (b N + N - 1) / 2; when that count is one short of tpt (odd N) the last tile is simply done twice.
   auto phys = [&](int lt) -> int {
-    if (!p.lig_only) return lt;
+    if (!LAST || !p.lig_only) return lt;
     const int b = lt / p.tpt, r = lt - b * p.tpt;
     const int base = b * p.N;
     return min(((base + p.R) >> 1) + r, (base + p.N - 1) >> 1);
@@ -385,10 +393,12 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
 #if EWS_PIN_ADDR
     asm volatile("" : "+r"(mlane), "+l"(tdrp_l), "+l"(totp_l));
 #endif
+    const bool full = !EWS_SKIP_PAD || (warp & 7) * 8 + 4 < p.K;     // second 4-row group holds real edge slots
     auto issue = [&](GBuf& g, uint32_t mslot, size_t aoff, int kb) {
       g.a = __ldg(reinterpret_cast<const uint4*>(p.Ahi + aoff + kb * 64));
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
+        if (i == 1 && !full) break;
         uint4 mt = lds128(mslot + mlane + (uint32_t)(4 * i) * 16u);
         if (EWS_EXP & 2) { mt.y = 0; mt.z = ((int)mt.z >= 0) ? 0u : mt.z; }
         g.td[i] = __ldg(reinterpret_cast<const uint4*>(tdrp_l + (size_t)mt.y * H + kb * 64));
@@ -400,6 +410,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
       const uint4 wr = lds128(vwr_s + (uint32_t)kb * 128u);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
+        if (i == 1 && !full) break;
         const uint32_t rad = lds32(mslot + mlane + (uint32_t)(4 * i) * 16u + 12u);
         const uint32_t sa = soff[i] + (uint32_t)kb * S_KBLK;
         const uint4 hb = lds128(sa);
@@ -666,7 +677,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         for (int k = 0; k < 4; ++k) gk[k] = __shfl_sync(0xffffffffu, g2, (lane & ~3) | k);
       }
       uint32_t sacc[16];
-      if (p.last) {
+      if (LAST) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -675,14 +686,18 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         if (node < p.total_nodes) {
           const int b = node / p.N, i = node - b * p.N;
           if (i >= p.R) {
+            // spill in fragment order: this lane's 16 column pairs of row k are 64 contiguous bytes at position
+            // ch*128 + cq*32 of the row (the Wc1 image is K-permuted to match, node.cu k_image_pack_perm): two 256-bit
+            // stores per row instead of sixteen 32-bit ones.  All 64 slots are written -- the pad slots' gate is 0.
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int slot = (q * 32 + rg + 8 * k) & 63;
-              if (slot < p.K) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + 2 * cq);
+              __half* dst = p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + cq * 32;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dst[j * 4] = m[k * 16 + j];
-              }
+              for (int v = 0; v < 2; ++v)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * v),
+                             "r"(m[k * 16 + 8 * v]), "r"(m[k * 16 + 8 * v + 1]), "r"(m[k * 16 + 8 * v + 2]), "r"(m[k * 16 + 8 * v + 3]),
+                             "r"(m[k * 16 + 8 * v + 4]), "r"(m[k * 16 + 8 * v + 5]), "r"(m[k * 16 + 8 * v + 6]), "r"(m[k * 16 + 8 * v + 7]) : "memory");
             }
           }
         }
@@ -758,13 +773,15 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
 #endif
   static unsigned long long attr_devices = 0;
   if (dfm_once_per_device(attr_devices, ctx->device)) {
-    CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(ews::k_edge_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ews::SMEM_ALLOC));
   }
   int grid = p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms;
   if (grid <= 0) return 0;
   p.chunk = (p.ntiles + grid - 1) / grid;
   grid = (p.ntiles + p.chunk - 1) / p.chunk;
-  ews::k_edge_ws<<<grid, ews::NT, ews::SMEM_ALLOC, s>>>(p);
+  if (p.last) CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<true>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p));
+  else CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<false>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p));
   LAUNCH_CHECK(ctx);
   return 0;
 }

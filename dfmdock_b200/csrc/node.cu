@@ -13,6 +13,19 @@ __global__ void k_image_pack(const float* __restrict__ W, int ldw, int col0, flo
   const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
   img[(((size_t)kb * 256 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(W[(size_t)n * ldw + col0 + k] * scale);
 }
+// Same image with K permuted into the edge epilogue's fragment order: position p = ch*128 + cq*32 + 2j + e holds column
+// c = ch*128 + 8j + 2cq + e (j = 0..15, cq = 0..3, e = 0..1) -- the order in which edge_ws.cu spills the gated messages.
+__global__ void k_image_pack_perm(const float* __restrict__ W, int ldw, float scale, __half* __restrict__ img) {
+  const int n = blockIdx.x, p = threadIdx.x;
+  const int q = p & 127, src = (p & 128) + 8 * ((q & 31) >> 1) + 2 * (q >> 5) + (q & 1);
+  const int kb = p >> 6, c = (p & 63) >> 3, e = p & 7;
+  img[(((size_t)kb * 256 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(W[(size_t)n * ldw + src] * scale);
+}
+int launch_image_pack_perm(dfm_ctx* ctx, const float* W, int ldw, float scale, __half* img, cudaStream_t s) {
+  k_image_pack_perm<<<256, 256, 0, s>>>(W, ldw, scale, img);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
 int launch_image_pack(dfm_ctx* ctx, const float* W, int ldw, int col0, float scale, __half* img, cudaStream_t s) {
   k_image_pack<<<256, 256, 0, s>>>(W, ldw, col0, scale, img);
   LAUNCH_CHECK(ctx);
@@ -145,6 +158,8 @@ __global__ void __launch_bounds__(256) k_graphnorm_silu(int N, const float* __re
 __global__ void __launch_bounds__(256) k_graphnorm_stats(int N, const float* __restrict__ z, const float* __restrict__ gw,
                                                         const float* __restrict__ gb, const float* __restrict__ gms,
                                                         float* __restrict__ gscale, float* __restrict__ gshift) {
+  pdl_trigger();            // programmatic dependent launch, see common.cuh
+  pdl_wait();
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const float* zb = z + (size_t)b * N * H;
   __shared__ float red[8][32];
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(256) k_graphnorm_stats(int N, const float* __r
 int launch_graphnorm_stats(dfm_ctx* ctx, int B, int layer, const float* z, float* gscale, float* gshift, cudaStream_t s) {
   const LayerW& w = ctx->layer[layer];
   dim3 grid(B, 8);
-  k_graphnorm_stats<<<grid, 256, 0, s>>>(ctx->N, z, w.gn_w, w.gn_b, w.gn_ms, gscale, gshift);
+  CUDA_TRY(dfm_launch_pdl(k_graphnorm_stats, grid, dim3(256), 0, s, ctx->N, z, w.gn_w, w.gn_b, w.gn_ms, gscale, gshift));
   LAUNCH_CHECK(ctx);
   return 0;
 }

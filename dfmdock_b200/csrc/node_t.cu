@@ -8,13 +8,16 @@
 //   MODE_Z   z = W3h h + W3a agg + b3                           node_mlp.0 on [h, agg]      (src/models/egnn.py:106-116)
 //   MODE_H   h += W4 SiLU(GraphNorm(z)) + b4  (+ fp16 copy)     node_mlp.1-3 + residual     (src/models/egnn.py:74,106-116)
 //
-// One persistent CTA per SM, 19 warps: 16 workers (epilogue; MODE_H also builds its operand), 2 cp.async loaders,
-// 1 MMA issuer.  Tiles are 64 rows (AB, H: two 128-feature halves -> 2 x 64 accumulator columns) or 128 rows (Z: one
+// One persistent CTA per SM, 19 warps: 16 workers (epilogue; MODE_H also builds its operand), 1 loader warp whose elected
+// thread issues one TMA tensor-map load (cp.async.bulk.tensor.2d, 64 columns x ROWS rows, SWIZZLE_128B, rows past M
+// zero-filled by the hardware) per K block, 1 MMA issuer.  Tiles are 64 rows (AB, H: two 128-feature halves -> 2 x 64 accumulator columns) or 128 rows (Z: one
 // 128-feature half of the output per grid half, K = 512); the operand ring holds 64 KB = 8 or 4 K blocks, the
 // accumulator (128 TMEM columns per tile) is quadruple buffered.
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ntt {
 
@@ -142,7 +145,8 @@ struct Params {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
+__global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p, const __grid_constant__ CUtensorMap tmX,
+                                                 const __grid_constant__ CUtensorMap tmX2) {
   // rows per tile = N of the MMA.  The issue path costs ~130 cycles per tcgen05.mma whatever its N (wait counters,
   // NTT_TIMING: with N = 64 the issuer was busy 87 % of MODE_AB while the tensor pipe was 16 % active), so MODE_AB uses
   // 128-row tiles like MODE_Z; MODE_H stays at 64 rows (its workers build the operand: not issue-bound)
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   static_assert(NSLOT <= 16, "barrier block holds 16 ring slots");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long t_kernel = clock64();
+  pdl_trigger();            // programmatic dependent launch, see common.cuh
 
   const int half_grid = (int)gridDim.x >> 1;
   const int side = (SPLIT && (int)blockIdx.x >= half_grid) ? 1 : 0;
@@ -187,7 +192,8 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 1); mbar_init(bar_empty + 8 * i, 1); }
+    if (MODE != MODE_H) { tma_prefetch_desc(&tmX); if (MODE == MODE_Z) tma_prefetch_desc(&tmX2); }
     for (int i = 0; i < NACCM; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
 #if NTT_BULK_W
     mbar_init(bar_w, 1);
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // activations written by the preceding kernels are complete and visible from here on
   const long long t_start = clock64();
   if (NTT_TIMING && tid == 0) atomicAdd(p.timing + 0, (unsigned long long)(t_start - t_kernel));
   unsigned long long tw0 = 0, tw1 = 0;
@@ -255,33 +262,21 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p) {
     }
     __syncwarp();
   } else if (warp >= NWORK) {
-    // =================================== LOADERS ======================================================
-    if (MODE != MODE_H) {
-      const int lw = warp - NWORK;                           // loader 0 takes even K blocks, loader 1 odd ones
-      const int c8 = lane & 7, rsub = lane >> 3;
+    // =================================== LOADER (TMA) =================================================
+    if (MODE != MODE_H && warp == NWORK && lane == 0) {
       uint32_t c = 0;
       for (int tile = cta; tile < p.ntiles; tile += ncta) {
         const int row0 = tile * ROWS;
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb, ++c) {
-          if ((kb & 1) != lw) continue;
           const uint32_t slot = c % NSLOT;
           if (c >= (uint32_t)NSLOT) NTWAIT(tw0, mbar_wait(bar_empty + 8 * slot, ((c / NSLOT) - 1) & 1u));
-          const __half* X = (MODE == MODE_Z && kb >= 4) ? p.X2 : p.X;
-          const int kcol = (kb & 3) * 64 + c8 * 8;
-          const uint32_t dst0 = sbase + OFF_S + slot * SLOT_BYTES;
-#pragma unroll 8
-          for (int i = 0; i < ROWS / 4; ++i) {
-            const int r = rsub + 4 * i;
-            const int m = row0 + r;
-            const bool ok = m < p.M;
-            cp_async16(dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4), X + (size_t)(ok ? m : 0) * H + kcol, ok ? 16u : 0u);
-          }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * slot) : "memory");
+          mbar_expect_tx(bar_full + 8 * slot, SLOT_BYTES);
+          tma_load_2d(sbase + OFF_S + slot * SLOT_BYTES, (MODE == MODE_Z && kb >= 4) ? &tmX2 : &tmX, (kb & 3) * 64, row0,
+                      bar_full + 8 * slot);
         }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      if (NTT_TIMING && warp == NWORK && lane == 0) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, (unsigned long long)(clock64() - t_start)); }
+      if (NTT_TIMING) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, (unsigned long long)(clock64() - t_start)); }
     }
     __syncwarp();
   } else {
@@ -408,12 +403,22 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
     CUDA_TRY(cudaFuncSetAttribute(k_nodeT<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
   }
   if (grid <= 0) return 0;
+  // tensor maps of the fp16 activation matrices [M, 256] (MODE_H builds its operand from fp32 z: no map needed)
+  constexpr int ROWS = (MODE == MODE_Z) ? NTT_Z_ROWS : (MODE == MODE_AB && NTT_AB_ROWS == 128) ? 128 : 64;
+  CUtensorMap tmX, tmX2;
+  memset(&tmX, 0, sizeof(tmX));
+  memset(&tmX2, 0, sizeof(tmX2));
+  if (MODE != MODE_H) {
+    int rc = dfm_make_tmap_f16(&tmX, p.X, (uint64_t)p.M, H, ROWS);
+    if (rc) return rc;
+    if (MODE == MODE_Z && (rc = dfm_make_tmap_f16(&tmX2, p.X2, (uint64_t)p.M, H, ROWS))) return rc;
+  }
 #if NTT_TIMING
   static unsigned long long* tbuf = nullptr;
   static int calls = 0;
   if (!tbuf) { CUDA_TRY(cudaMalloc(&tbuf, 64)); CUDA_TRY(cudaMemset(tbuf, 0, 64)); }
   Params q = p; q.timing = tbuf;
-  k_nodeT<MODE><<<grid, NT, SMEM_ALLOC, s>>>(q);
+  CUDA_TRY(dfm_launch_pdl(k_nodeT<MODE>, dim3(grid), dim3(NT), SMEM_ALLOC, s, q, tmX, tmX2));
   if (++calls % 16 == 0) {
     unsigned long long hb[8];
     cudaMemcpy(hb, tbuf, 64, cudaMemcpyDeviceToHost);
@@ -424,7 +429,7 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
   LAUNCH_CHECK(ctx);
   return 0;
 #endif
-  k_nodeT<MODE><<<grid, NT, SMEM_ALLOC, s>>>(p);
+  CUDA_TRY(dfm_launch_pdl(k_nodeT<MODE>, dim3(grid), dim3(NT), SMEM_ALLOC, s, p, tmX, tmX2));
   LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -2,14 +2,19 @@
 //   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2),  f_i = mean_k (x_i - x_j) / (|x_i - x_j| + 1) w      (src/models/egnn.py:118-148)
 // m* = the gated messages edge_ws.cu spills for the ligand residues, [B*L, 64 slots, 256] fp16 (x 2^-6).
 //
+// The spill is stored with the columns of each 128-column half in the epilogue's fragment order (edge_ws.cu, position
+// cq*32 + 2j + e <-> column 8j + 2cq + e, so that a thread stores 64 contiguous bytes); the image of Wc1 carries the same
+// permutation along K (launch_image_pack_perm), so the contraction is unchanged.
+//
 // One persistent CTA per SM, 19 warps:
 //   warps 0-15  workers: epilogue from TMEM (SiLU, dot with wc2, clamp, displacement, mean over the 60 slots)
-//   warps 16-17 loaders: the tile's K blocks HBM -> shared memory with cp.async, straight into the K-major SWIZZLE_128B
-//               operand layout, one 64-column K block (16 KB) at a time into a ring of four blocks
+//   warp  16    loader: one elected thread issues one TMA tensor-map load (cp.async.bulk.tensor.2d, 64 columns x 128 rows,
+//               SWIZZLE_128B) per K block into a ring of five 16 KB slots -- 80 KB in flight per SM, what HBM latency needs
 //   warp  18    MMA issuer: one tcgen05.commit per K block (frees the ring slot) and one per tile (accumulator ready)
 // The 128 KB fp16 image of Wc1 (x 2^6) is resident in shared memory; accumulators are double buffered in TMEM.
 // (The other node-side contractions live in node_t.cu.)
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ntc {
 
@@ -17,11 +22,13 @@ constexpr int TILE_M = 128;
 constexpr uint32_t W_BYTES = 256 * 256 * 2;          // 128 KB in every mode (256 x 256 or 128 x 512 fp16)
 constexpr uint32_t S_KBLK = TILE_M * 128;            // one K block of the operand tile: 128 rows x 64 fp16
 constexpr uint32_t OFF_W = 0;
-constexpr uint32_t OFF_S = W_BYTES;                  // ring of 4 K blocks
-constexpr uint32_t OFF_VEC = OFF_S + 4 * S_KBLK;     // 256 floats bias, 256 floats wc2
-constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // MODE_C: [4][128] dot partials, [4][4] force partials
-constexpr uint32_t OFF_BAR = OFF_PART + 2048 + 64;   // full[4], empty[4], accf[2], acce[2], tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+constexpr int NSLOT = 5;                             // ring slots (K blocks of 16 KB)
+constexpr uint32_t OFF_S = W_BYTES;                  // ring of NSLOT K blocks
+constexpr uint32_t OFF_VEC = OFF_S + NSLOT * S_KBLK; // 256 floats bias, 256 floats wc2
+constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [2][4][128] dot partials, [2][4][4] force partials
+constexpr uint32_t OFF_BAR = OFF_PART + 4096 + 128;   // full[8], empty[8], accf[2], acce[2], w, tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 192;
+static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;
 constexpr int NWORK = 16;
 constexpr int NT = (NWORK + 3) * 32;                 // 608
@@ -104,7 +111,7 @@ struct Params {
   int R, K;
 };
 
-__global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
+__global__ void __launch_bounds__(NT, 1) k_coord(const Params p, const __grid_constant__ CUtensorMap tmX) {
   constexpr int KB = 4;                                   // K blocks per tile
   constexpr int NCOL = 256;                               // accumulator columns per tile
   constexpr uint32_t W_KBLK = NCOL * 128;                 // bytes per K block of the weight image
@@ -114,22 +121,24 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* vbias = reinterpret_cast<float*>(smem + OFF_VEC);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
-  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 32;
-  const uint32_t bar_accf = sbase + OFF_BAR + 64, bar_acce = sbase + OFF_BAR + 80;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 176);
+  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = sbase + OFF_BAR + 64;
+  const uint32_t bar_accf = sbase + OFF_BAR + 128, bar_acce = sbase + OFF_BAR + 144;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+  pdl_trigger();            // programmatic dependent launch, see common.cuh
 
   // ---- setup: weight image (four bulk copies, async proxy; only the MMA issuer waits for them), vectors, barriers, TMEM
-  const uint32_t bar_w = sbase + OFF_BAR + 96;
+  const uint32_t bar_w = sbase + OFF_BAR + 160;
   if (tid < 256) {
     vbias[tid] = p.bias0[tid];
     vbias[256 + tid] = p.wc2[tid];
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
     mbar_init(bar_w, 1);
+    tma_prefetch_desc(&tmX);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(W_BYTES) : "memory");
     const char* wsrc = reinterpret_cast<const char*>(p.W0);
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // the edge kernel's spill is complete and visible from here on
 
   if (warp == NWORK + 2) {
     // =================================== MMA ISSUER ===================================================
@@ -162,8 +172,8 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NCOL);
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb, ++c) {
-          const uint32_t slot = c & 3u;
-          mbar_wait(bar_full + 8 * slot, (c >> 2) & 1u);
+          const uint32_t slot = c % NSLOT;
+          mbar_wait(bar_full + 8 * slot, (c / NSLOT) & 1u);
           tc_fence_after();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -178,31 +188,20 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
     }
     __syncwarp();
   } else if (warp >= NWORK) {
-    // =================================== LOADERS ======================================================
-    const int lw = warp - NWORK;                           // loader 0 takes even K blocks, loader 1 odd ones
-    const int c8 = lane & 7, rsub = lane >> 3;
-    uint32_t c = 0;
-    for (int tile = cta; tile < p.ntiles; tile += ncta) {
-      const int row0 = tile * TILE_M;
+    // =================================== LOADER (TMA) =================================================
+    if (warp == NWORK && lane == 0) {
+      uint32_t c = 0;
+      for (int tile = cta; tile < p.ntiles; tile += ncta) {
+        const int row0 = tile * TILE_M;
 #pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb, ++c) {
-        if ((kb & 1) != lw) continue;
-        const uint32_t slot = c & 3u;
-        if (c >= 4) mbar_wait(bar_empty + 8 * slot, ((c >> 2) - 1) & 1u);
-        const int kcol = kb * 64 + c8 * 8;
-        const uint32_t dst0 = sbase + OFF_S + slot * S_KBLK;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int r = rsub + 4 * i;
-          const int m = row0 + r;
-          // pad slots (K..63) are never written by the edge kernel: zero-fill them instead of reading stale memory
-          const bool ok = m < p.M && (r & 63) < p.K;
-          cp_async16(dst0 + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4), p.X + (size_t)(ok ? m : 0) * H + kcol, ok ? 16u : 0u);
+        for (int kb = 0; kb < KB; ++kb, ++c) {
+          const uint32_t slot = c % NSLOT;
+          if (c >= (uint32_t)NSLOT) mbar_wait(bar_empty + 8 * slot, ((c / NSLOT) - 1) & 1u);
+          mbar_expect_tx(bar_full + 8 * slot, S_KBLK);
+          tma_load_2d(sbase + OFF_S + slot * S_KBLK, &tmX, kb * 64, row0, bar_full + 8 * slot);
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * slot) : "memory");
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
   } else {
     // =================================== WORKERS ======================================================
@@ -210,7 +209,35 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
     const int erow = q * 32 + lane;
     constexpr int CW = NCOL / 4;                             // accumulator columns per thread (64)
 
-    auto epilogue = [&](int tile, int buf) {
+    const uint32_t vb_s = sbase + OFF_VEC + (uint32_t)(cq * CW) * 4u;      // bc1 / wc2 of this thread's 64 columns (shared space)
+    const int total = p.M / SLOTS;                                          // B * L ligand residues
+    const int L = p.N - p.R;
+    float* part = reinterpret_cast<float*>(smem + OFF_PART);                // [2 tile parities][4 column quarters][128 rows]
+    float* fpart = part + 1024;                                             // [2][4 row quarters][4]
+
+    int it = 0;
+    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+      const int buf = it & 1;
+      // geometry of this row's edge, fetched BEFORE the accumulator is waited for (it does not depend on the MMA; the
+      // nbr -> pos dependent loads used to sit between two CTA-wide barriers and cost ~2 k cycles per tile):
+      // g = (x_i - x_j) / ((|x_i - x_j| + 1) K), row `erow` of the tile = slot erow & 63 of ligand residue tile*2 + (erow >> 6)
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      if (cq == 0) {
+        const int node = tile * 2 + (erow >> 6), k = erow & 63;
+        if (node < total && k < p.K) {
+          const int b = node / L, i = p.R + node % L;
+          const size_t gi = (size_t)b * p.N + i;
+          const int j = __ldg(p.nbr + gi * SLOTS + k);
+          const float* pi = p.pos + gi * 9 + 3;
+          const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
+          const float dx = __ldg(pi) - __ldg(pj), dy = __ldg(pi + 1) - __ldg(pj + 1), dz = __ldg(pi + 2) - __ldg(pj + 2);
+          const float rad = dx * dx + dy * dy + dz * dz;
+          const float sc = 1.f / ((sqrtf(rad + 1e-8f) + 1.0f) * (float)p.K);
+          gx = dx * sc; gy = dy * sc; gz = dz * sc;
+        }
+      }
+      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NCOL + cq * CW);
       float dotp = 0.f;
 #pragma unroll
@@ -222,56 +249,40 @@ __global__ void __launch_bounds__(NT, 1) k_coord(const Params p) {
           tc_fence_before();
           mbar_arrive(bar_acce + 8 * buf);
         }
-        const int col0 = cq * CW + c * 32;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) dotp = fmaf(silu_tanh(v[e] + vbias[col0 + e]), vbias[256 + col0 + e], dotp);
-      }
-      // tile = 2 ligand residues x 64 slots: clamp(dot) -> displacement along x_i - x_j -> mean over the K slots
-      float* part = reinterpret_cast<float*>(smem + OFF_PART);
-      float* fpart = part + 512;
-      const int total = p.M / SLOTS;                       // B * L residues
-      const int node = tile * 2 + (erow >> 6), k = erow & 63;
-      const bool valid = node < total && k < p.K;
-      part[cq * 128 + erow] = dotp;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      float fx = 0.f, fy = 0.f, fz = 0.f;
-      if (cq == 0 && valid) {
-        const float tot = (part[erow] + part[128 + erow]) + (part[256 + erow] + part[384 + erow]);
-        const int L = p.N - p.R;
-        const int b = node / L, i = p.R + node % L;
-        const size_t gi = (size_t)b * p.N + i;
-        const int j = __ldg(p.nbr + gi * SLOTS + k);
-        const float* pi = p.pos + gi * 9 + 3;
-        const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
-        const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
-        const float rad = dx * dx + dy * dy + dz * dz;
-        const float sc = fminf(fmaxf(tot, -2.f), 2.f) / (sqrtf(rad + 1e-8f) + 1.0f);
-        fx = dx * sc; fy = dy * sc; fz = dz * sc;
-      }
-      if (cq == 0) {
-        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-        if (lane == 0) { fpart[q * 4] = fx; fpart[q * 4 + 1] = fy; fpart[q * 4 + 2] = fz; }
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tid < 2) {
-        const int nd = tile * 2 + tid;
-        if (nd < total) {
-          const float inv = 1.f / (float)p.K;
-          float* fo = p.fbuf + (size_t)nd * 4;
-          fo[0] = (fpart[(2 * tid) * 4] + fpart[(2 * tid + 1) * 4]) * inv;
-          fo[1] = (fpart[(2 * tid) * 4 + 1] + fpart[(2 * tid + 1) * 4 + 1]) * inv;
-          fo[2] = (fpart[(2 * tid) * 4 + 2] + fpart[(2 * tid + 1) * 4 + 2]) * inv;
-          fo[3] = 0.f;
+        for (int e4 = 0; e4 < 8; ++e4) {
+          float4 bb, ww;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(vb_s + (uint32_t)(c * 32 + e4 * 4) * 4u));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ww.x), "=f"(ww.y), "=f"(ww.z), "=f"(ww.w) : "r"(vb_s + 1024u + (uint32_t)(c * 32 + e4 * 4) * 4u));
+          dotp = fmaf(silu_tanh(v[e4 * 4] + bb.x), ww.x, dotp);
+          dotp = fmaf(silu_tanh(v[e4 * 4 + 1] + bb.y), ww.y, dotp);
+          dotp = fmaf(silu_tanh(v[e4 * 4 + 2] + bb.z), ww.z, dotp);
+          dotp = fmaf(silu_tanh(v[e4 * 4 + 3] + bb.w), ww.w, dotp);
         }
       }
-    };
-
-    int it = 0;
-    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
-      const int buf = it & 1;
-      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      epilogue(tile, buf);
+      // the four column quarters of a row meet in shared memory (double buffered by tile parity: only the cq == 0 warps
+      // go on to the reduction, the other twelve move straight to the next tile)
+      part[buf * 512 + cq * 128 + erow] = dotp;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (cq == 0) {
+        const float* pp = part + buf * 512;
+        const float tot = (pp[erow] + pp[128 + erow]) + (pp[256 + erow] + pp[384 + erow]);
+        const float w = fminf(fmaxf(tot, -2.f), 2.f);
+        const float fx = warp_sum(gx * w), fy = warp_sum(gy * w), fz = warp_sum(gz * w);
+        float* fp = fpart + buf * 16;
+        if (lane == 0) { fp[q * 4] = fx; fp[q * 4 + 1] = fy; fp[q * 4 + 2] = fz; }
+        asm volatile("bar.sync 2, 128;" ::: "memory");          // the four row-quarter warps
+        if (tid < 2) {
+          const int nd = tile * 2 + tid;
+          if (nd < total) {
+            float* fo = p.fbuf + (size_t)nd * 4;
+            fo[0] = fp[(2 * tid) * 4] + fp[(2 * tid + 1) * 4];
+            fo[1] = fp[(2 * tid) * 4 + 1] + fp[(2 * tid + 1) * 4 + 1];
+            fo[2] = fp[(2 * tid) * 4 + 2] + fp[(2 * tid + 1) * 4 + 2];
+            fo[3] = 0.f;
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -287,7 +298,10 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
     CUDA_TRY(cudaFuncSetAttribute(k_coord, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
   }
   if (grid <= 0) return 0;
-  k_coord<<<grid, NT, SMEM_ALLOC, s>>>(p);
+  CUtensorMap tmX;
+  int rc = dfm_make_tmap_f16(&tmX, p.X, (uint64_t)p.M, H, TILE_M);
+  if (rc) return rc;
+  CUDA_TRY(dfm_launch_pdl(k_coord, dim3(grid), dim3(NT), SMEM_ALLOC, s, p, tmX));
   LAUNCH_CHECK(ctx);
   return 0;
 }
