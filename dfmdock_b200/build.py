@@ -29,7 +29,7 @@ def _stale(target, deps):
 
 def build_library(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dfmdock_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(HERE, "..", "include", "dfmdock_b200.h")]
     nvcc = _nvcc()
     extra = os.environ.get("DFM_NVCC_EXTRA", "").split()      # experiment switches, e.g. -DEWS_USE_ALO=0
     objs = []

@@ -32,6 +32,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ews {
 
@@ -46,8 +47,7 @@ constexpr uint32_t OFF_VEC = OFF_S + S_BYTES;        // (1 KB spare), w1r' [256]
 constexpr uint32_t OFF_PART = OFF_VEC + 2048;        // [<=4 column groups][128 rows] float gate partials
 constexpr uint32_t OFF_AGG = OFF_PART + 4 * 128 * 4; // [2 tile parities][4 lane quarters][256] float column sums
 constexpr uint32_t OFF_META = OFF_AGG + 2 * 4 * 256 * 4; // [16 producer warps][2 slots][8 rows] int4 edge metadata
-constexpr uint32_t OFF_JRING = OFF_META + 16 * 2 * 8 * 16; // [2 loader warps][2 slots][128 rows] int32 global row of j
-constexpr uint32_t OFF_VEC32 = OFF_JRING + 2 * 2 * 128 * 4; // fragment-ordered b2/2 and wa as half2: [2 halves][4 t%4][20-word rows] each
+constexpr uint32_t OFF_VEC32 = OFF_META + 16 * 2 * 8 * 16; // fragment-ordered b2/2 and wa as half2: [2 halves][4 t%4][20-word rows] each
 constexpr uint32_t OFF_BAR = OFF_VEC32 + 2048;            // 16 mbarriers + tmem base
 // b2 folded into the accumulator by one extra K = 16 MMA per tile: A = [128 x 16] of 1/16, B = [256 x 16] with row n = b2[n]/2
 // (both K-major, no swizzle: 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row groups 256 B apart)
@@ -268,7 +268,7 @@ __device__ __forceinline__ void lane_group_sum_h2(uint32_t* v, int lane) {
 // LAST: the last E_GCL layer (spill of the ligand rows' gated messages for the coordinate head, optional ligand-only tile walk);
 // a separate instantiation so that the five other launches carry neither its code nor its registers
 template <bool LAST>
-__global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
+__global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, 32);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, 1);
+    tma_prefetch_desc(&tmB);
 #if EWS_BULK_W
     mbar_init(bar_w, 1);
 #endif
@@ -517,63 +518,39 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p) {
         if (EWS_TIMING) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, tw1); }
       }
     } else if (warp <= NPROD + NEPI + 2) {
-      // Loader warp lw (0/1) copies the B_j rows of K blocks lw and lw+2 of every tile straight into the S tile with
-      // cp.async (16 bytes per lane and instruction, no registers held while in flight); the producers add the rest
-      // in place.  A block may be refilled as soon as the MMA of the previous tile has consumed it (bar_empty).
+      // Loader warp lw (0/1) brings the B_j rows of K blocks lw and lw+2 of every tile straight into the S tile with TMA:
+      // lane l issues one cp.async.bulk.tensor.2d tile::gather4 per K block (rows 4l..4l+3 of the tile = four neighbour
+      // rows of Bm, 64 columns each, SWIZZLE_128B), completion by transaction bytes on bar_bfull.  No registers are held
+      // while the rows are in flight and nothing passes through the LSU / L1 pipe; the producers add the rest in place.
+      // A block may be refilled as soon as the MMA of the previous tile has consumed it (bar_empty).
       const int lw = warp - (NPROD + NEPI + 1);
-      // j ring: [2 slots][4 row residues][32] -> the 32 rows (rsub + 4 i) of one lane are contiguous (8 x LDS.128)
-      const uint32_t jring_s = sbase + OFF_JRING + (uint32_t)lw * 1024u;
-      const int c8 = lane & 7, rsub = lane >> 3;
-      auto load_j = [&](int ptile, bool inrange, int i) -> int {   // global row of the neighbour of tile row lane + 32 i
-        const int r = lane + 32 * i;
-        const int node = ptile * 2 + (r >> 6);
-        int j = 0;
-        if (inrange && node < p.total_nodes) j = __ldg(reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + (r & 63)));
+      auto load_j4 = [&](int ptile, bool inrange) -> int4 {   // global rows of the neighbours of tile rows 4 lane .. 4 lane + 3
+        const int node = ptile * 2 + (lane >> 4);
+        int4 j = make_int4(0, 0, 0, 0);
+        if (inrange && node < p.total_nodes) {
+          const int* e = reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + ((4 * lane) & 63));
+          j.x = __ldg(e); j.y = __ldg(e + 4); j.z = __ldg(e + 8); j.w = __ldg(e + 12);
+        }
         return j;
       };
-      // row r = lane + 32 i sits at ring index (r & 3) * 32 + (r >> 2)
-      const uint32_t jput = (uint32_t)((lane & 3) * 32 + (lane >> 2)) * 4u;
-      if (t_begin < t_end) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jring_s + jput + (uint32_t)i * 32u, (uint32_t)load_j(phys(t_begin), true, i));
-      }
-      __syncwarp();
-      // destination of this lane's chunk in row rsub + 4 i: (rsub + 4 i) * 128 + ((c8 ^ ((rsub + 4 i) & 7)) << 4);
-      // (rsub + 4 i) & 7 alternates between rsub and rsub + 4 -> two swizzled chunk offsets
-      const uint32_t dsw0 = (uint32_t)((c8 ^ rsub) << 4), dsw1 = (uint32_t)((c8 ^ (rsub + 4)) << 4);
-      const char* srcb = reinterpret_cast<const char*>(p.Bm) + c8 * 16;
+      int4 jc = make_int4(0, 0, 0, 0);
+      if (t_begin < t_end) jc = load_j4(phys(t_begin), true);
+      const uint32_t dst_lane = sbase + OFF_S + (uint32_t)lane * 512u;
       unsigned long long tw0 = 0;
       const long long tstart = clock64();
       int it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const uint32_t jc = jring_s + (uint32_t)(it & 1) * 512u + (uint32_t)rsub * 128u;
-        int jn[4];
         const bool nin = tile + 1 < t_end;
-        const int nptile = nin ? phys(tile + 1) : 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) jn[i] = load_j(nptile, nin, i);
+        const int4 jn = load_j4(nin ? phys(tile + 1) : 0, nin);
 #pragma unroll 1
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = lw + 2 * kk;
           if (it > 0) TWAIT(tw0, mbar_wait<EWS_SLEEP_L>(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1)));
-          const char* src0 = srcb + kb * 128;
-          const uint32_t dst0 = sbase + OFF_S + (uint32_t)kb * S_KBLK + (uint32_t)rsub * 128u;
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            uint4 j4 = lds128(jc + (uint32_t)i4 * 16u);
-            if (EWS_EXP & 1) j4 = make_uint4(0, 0, 0, 0);
-            const uint32_t d = dst0 + (uint32_t)i4 * 2048u;      // rows rsub + 16 i4 + {0, 4, 8, 12}
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + dsw0), "l"(src0 + (size_t)j4.x * 512) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u + dsw1), "l"(src0 + (size_t)j4.y * 512) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1024u + dsw0), "l"(src0 + (size_t)j4.z * 512) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1536u + dsw1), "l"(src0 + (size_t)j4.w * 512) : "memory");
-          }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_bfull + 8 * kb) : "memory");
+          if (lane == 0) mbar_expect_tx(bar_bfull + 8 * kb, S_KBLK);
+          __syncwarp();
+          tma_gather4_2d(dst_lane + (uint32_t)kb * S_KBLK, &tmB, kb * 64, jc.x, jc.y, jc.z, jc.w, bar_bfull + 8 * kb);
         }
-        const uint32_t jnx = jring_s + (uint32_t)((it & 1) ^ 1) * 512u + jput;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sts32(jnx + (uint32_t)i * 32u, (uint32_t)jn[i]);
-        __syncwarp();
+        jc = jn;
       }
       if (EWS_TIMING && lw == 0 && lane == 0) { atomicAdd(p.timing + 2, tw0); atomicAdd(p.timing + 3, (unsigned long long)(clock64() - tstart)); }
     }
@@ -780,8 +757,12 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   if (grid <= 0) return 0;
   p.chunk = (p.ntiles + grid - 1) / grid;
   grid = (p.ntiles + p.chunk - 1) / p.chunk;
-  if (p.last) CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<true>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p));
-  else CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<false>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p));
+  // Bm as a rank-2 tensor {256 columns, B*N rows}; box = 64 columns x 1 row, four rows per tile::gather4 instruction
+  CUtensorMap tmB;
+  int rc = dfm_make_tmap_f16(&tmB, p.Bm, (uint64_t)p.total_nodes, H, 1);
+  if (rc) return rc;
+  if (p.last) CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<true>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p, tmB));
+  else CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<false>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p, tmB));
   LAUNCH_CHECK(ctx);
   return 0;
 }

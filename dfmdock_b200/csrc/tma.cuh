@@ -53,6 +53,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// tile::gather4: four rows {r0..r3} of the rank-2 tensor (box = 64 columns x 1 row), columns c0..c0+63, land as four
+// consecutive 128-byte rows at smem_dst (512-byte aligned inside a 1024-byte aligned SWIZZLE_128B tile); completes
+// 512 bytes on the mbarrier
+__device__ __forceinline__ void tma_gather4_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3,
+                                               uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
