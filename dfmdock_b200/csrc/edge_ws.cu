@@ -103,6 +103,12 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_SLEEP_E
 #define EWS_SLEEP_E 200
 #endif
+#ifndef EWS_LOAD_BYKB
+#define EWS_LOAD_BYKB 0    // 1: loader warp lw takes whole K blocks lw, lw + EWS_NLOAD, ..; 0: every loader warp takes a share of the rows of every K block
+#endif
+#ifndef EWS_NLOAD
+#define EWS_NLOAD 3        // B_j loader warps (1..3): the 32 gather units of a K block are split over them
+#endif
 #ifndef EWS_BULK_W
 #define EWS_BULK_W 1      // weight image by cp.async.bulk (TMA 1-D), overlapped with the rest of the set-up and the first tile's build
 #endif
@@ -139,6 +145,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #else
 #define TWAIT(acc, call) do { call; } while (0)
 #endif
+#ifndef EWS_WAIT_HINT
+#define EWS_WAIT_HINT 1   // 1: retries park inside try_wait with a suspend-time hint (no poll instructions while parked); 0: nanosleep back-off
+#endif
 template <int SLEEP_NS = 40>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, tries = 0;
@@ -146,11 +155,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   while (!ok) {
+#if EWS_WAIT_HINT
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (++tries > (1u << 20)) __trap();
+#else
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (++tries > (1u << 24)) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, EWS_LOAD_BYKB ? 1 : EWS_NLOAD);
     tma_prefetch_desc(&tmB);
 #if EWS_BULK_W
     mbar_init(bar_w, 1);
@@ -517,25 +533,31 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
         }
         if (EWS_TIMING) { atomicAdd(p.timing + 4, tw0); atomicAdd(p.timing + 5, tw1); }
       }
-    } else if (warp <= NPROD + NEPI + 2) {
-      // Loader warp lw (0/1) brings the B_j rows of K blocks lw and lw+2 of every tile straight into the S tile with TMA:
-      // lane l issues one cp.async.bulk.tensor.2d tile::gather4 per K block (rows 4l..4l+3 of the tile = four neighbour
-      // rows of Bm, 64 columns each, SWIZZLE_128B), completion by transaction bytes on bar_bfull.  No registers are held
-      // while the rows are in flight and nothing passes through the LSU / L1 pipe; the producers add the rest in place.
-      // A block may be refilled as soon as the MMA of the previous tile has consumed it (bar_empty).
+    } else if (warp <= NPROD + NEPI + EWS_NLOAD) {
+      // Loader warps bring the B_j rows of every K block of every tile straight into the S tile with TMA: one
+      // cp.async.bulk.tensor.2d tile::gather4 per four tile rows (four neighbour rows of Bm, 64 columns each,
+      // SWIZZLE_128B), completion by transaction bytes on bar_bfull.  No registers are held while the rows are in flight and
+      // nothing passes through the LSU / L1 pipe; the producers add the rest in place.  A block may be refilled as soon as
+      // the MMA of the previous tile has consumed it (bar_empty).  The 32 four-row units of a K block are split over the
+      // EWS_NLOAD loader warps (the per-lane TMA issue is serialised by the hardware's uniform-operand rule, so the split
+      // shortens the refill latency of a block, which sits on the build -> MMA -> refill -> build cycle of the S tile).
       const int lw = warp - (NPROD + NEPI + 1);
-      auto load_j4 = [&](int ptile, bool inrange) -> int4 {   // global rows of the neighbours of tile rows 4 lane .. 4 lane + 3
-        const int node = ptile * 2 + (lane >> 4);
+      constexpr int UPW = EWS_LOAD_BYKB ? 32 : (32 + EWS_NLOAD - 1) / EWS_NLOAD;          // units per loader warp
+      const int unit = EWS_LOAD_BYKB ? lane : lw * UPW + lane;                              // this lane's four-row unit (tile rows 4 unit ..)
+      const bool act = lane < UPW && unit < 32 && !((EWS_EXP & 8) && (unit & 1));
+      const uint32_t nact = (EWS_EXP & 8) ? (uint32_t)__popc(__ballot_sync(0xffffffffu, act)) : (uint32_t)(EWS_LOAD_BYKB ? 32 : min(UPW, 32 - lw * UPW));   // active lanes of this warp
+      auto load_j4 = [&](int ptile, bool inrange) -> int4 {   // global rows of the neighbours of tile rows 4 unit .. 4 unit + 3
+        const int node = ptile * 2 + (unit >> 4);
         int4 j = make_int4(0, 0, 0, 0);
-        if (inrange && node < p.total_nodes) {
-          const int* e = reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + ((4 * lane) & 63));
+        if (act && inrange && node < p.total_nodes) {
+          const int* e = reinterpret_cast<const int*>(p.emeta + (size_t)node * SLOTS + ((4 * unit) & 63));
           j.x = __ldg(e); j.y = __ldg(e + 4); j.z = __ldg(e + 8); j.w = __ldg(e + 12);
         }
         return j;
       };
       int4 jc = make_int4(0, 0, 0, 0);
       if (t_begin < t_end) jc = load_j4(phys(t_begin), true);
-      const uint32_t dst_lane = sbase + OFF_S + (uint32_t)lane * 512u;
+      const uint32_t dst_lane = sbase + OFF_S + (uint32_t)unit * 512u;
       unsigned long long tw0 = 0;
       const long long tstart = clock64();
       int it = 0;
@@ -543,12 +565,11 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
         const bool nin = tile + 1 < t_end;
         const int4 jn = load_j4(nin ? phys(tile + 1) : 0, nin);
 #pragma unroll 1
-        for (int kk = 0; kk < 2; ++kk) {
-          const int kb = lw + 2 * kk;
+        for (int kb = EWS_LOAD_BYKB ? lw : 0; kb < 4; kb += EWS_LOAD_BYKB ? EWS_NLOAD : 1) {
           if (it > 0) TWAIT(tw0, mbar_wait<EWS_SLEEP_L>(bar_empty + 8 * kb, (uint32_t)((it - 1) & 1)));
-          if (lane == 0) mbar_expect_tx(bar_bfull + 8 * kb, S_KBLK);
+          if (lane == 0) mbar_expect_tx(bar_bfull + 8 * kb, nact * 512u);
           __syncwarp();
-          tma_gather4_2d(dst_lane + (uint32_t)kb * S_KBLK, &tmB, kb * 64, jc.x, jc.y, jc.z, jc.w, bar_bfull + 8 * kb);
+          if (act) tma_gather4_2d(dst_lane + (uint32_t)kb * S_KBLK, &tmB, kb * 64, jc.x, jc.y, jc.z, jc.w, bar_bfull + 8 * kb);
         }
         jc = jn;
       }
