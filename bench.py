@@ -393,25 +393,25 @@ def run_cuda(args):
 
     # ---- end-to-end through the public API with host buffers -----------------------------------------
     lig, tr_u, rot_u = st["lig"], st["tr_u"], st["rot_u"]
-    lig_host = torch.empty(B, L, 3, 3).pin_memory()
+    # two pinned pose buffers used in turn: the pose a step returns to the host is the pose the next step sends to the device
+    pose_host = [torch.empty(B, L, 3, 3).pin_memory(), torch.empty(B, L, 3, 3).pin_memory()]
     t_host = torch.empty(B).pin_memory()
-    out_host = torch.empty(B, L, 3, 3).pin_memory()
     sc_host = torch.empty(B, 6).pin_memory()
-    lig_host.copy_(lig.cpu())
+    pose_host[1].copy_(lig.cpu())
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step(k):
         t = float(ts[half + k % (S - 1 - half)])
         t_host.fill_(t)
-        lig_d = lig_host.to(dev, non_blocking=True)
+        src, dst = pose_host[(k + 1) & 1], pose_host[k & 1]
+        lig_d = src.to(dev, non_blocking=True)
         t_d = t_host.to(dev, non_blocking=True)
         o = model.score(lig_d, t_d, seed=args.seed, stream_base=base, forward_index=1000 + k)
         model.reverse_step(lig_d, rot_u, tr_u, o["tr_score"], o["rot_score"], t, dt, 0.5, 0.5, seed=args.seed,
                            stream_base=base, step_index=1000 + k)
-        out_host.copy_(lig_d, non_blocking=True)
+        dst.copy_(lig_d, non_blocking=True)
         sc_host.copy_(torch.cat([o["tr_score"], o["rot_score"]], dim=1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()      # the caller reads the result of every step
-        lig_host.copy_(out_host)
 
     e2e_step(0)
     sync_all()
