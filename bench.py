@@ -445,8 +445,9 @@ def run_cuda(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        # five launches per forward walk every edge, the sixth only the ligand residues' edges: average work per launch
-        executed = (5.0 + last_layer_row_fraction(N, N_REC)) / 6.0
+        # timed: the five launches of a forward that walk every edge (the sixth walks only the ligand residues' tiles and,
+        # fused with the coordinate head, is not an edge-kernel sample)
+        executed = 1.0
         flops_launch = edge_kernel_flops_per_launch(B, N) * executed
         edge_avg_ms = edge_ms / max(edge_n, 1)
         achieved = flops_launch / (edge_avg_ms * 1e-3) / 1e12 if edge_n else None
@@ -479,8 +480,8 @@ def run_cuda(args):
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
                          "traffic": traffic, "peak_source": peaks["source"], "kernel_ms_per_launch": edge_avg_ms,
                          "launches_timed": edge_n, "flops_per_launch": flops_launch,
-                         "flops_note": "average over the 6 launches of a forward of the edges each launch actually processes "
-                                       "(5 x all edges + 1 x the ligand residues' edges = %.4f of 6 full launches)" % executed,
+                         "flops_note": "the 5 launches of a forward that walk every edge (B x N x 60 edges x (2 x 256^2 + 2 x 256) flop); the "
+                                       "last layer's ligand-only launch (fused with the coordinate head) is not in the sample",
                          "kernel_share_of_step": (edge_ms / elapsed_ms) if edge_n else None,
                          "whole_step_tflops": step_flops / (elapsed_ms / args.steps * 1e-3) / 1e12},
             "strong_scaling": strong_line,

@@ -17,6 +17,7 @@ NOISE_ANNEAL = 1 << 3
 CENTRE_ALL_ATOMS = 1 << 4
 ODE = 1 << 5
 GRAPH_GENERIC = 1 << 6
+LAST_FUSED = 1 << 7
 EDGE_SLOTS = 64
 
 # name -> (restype, argtypes); mirrors include/dfmdock_b200.h one to one

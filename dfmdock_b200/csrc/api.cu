@@ -63,6 +63,7 @@ Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base) {
   w.agg16 = (__half*)take(b * N * H * 2);
   w.gscale = (float*)take(b * H * 4);
   w.gshift = (float*)take(b * H * 4);
+  w.ring_flags = (unsigned int*)take(RING_FLAG_WORDS * 4);
   w.bytes = off;
   return w;
 }
@@ -335,14 +336,18 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
     ea.lig_only = last && !want_energy;   // the receptor rows' layer-5 messages only feed the node update the energy head needs
     ea.nbr = ws.nbr; ea.feat = ws.feat; ea.radial = ws.radial; ea.A = ws.A; ea.Bm = ws.Bm; ea.pos = ws.pos;
     ea.agg = ws.agg; ea.mstar = ws.mstar; ea.fbuf = ws.fbuf;
-    const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_events.size();
+    // timed launches (dfm_profile_*): the five full-size launches of a forward; the last layer's launch walks only the
+    // ligand tiles and may carry the coordinate head (k_last_fused), so it is not an edge-kernel sample
+    const bool prof = ctx->profile && !last && ctx->prof_used + 2 <= ctx->prof_events.size();
     if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used], s));
-    if ((rc = launch_edge_ws(ctx, ea, ws.emeta, Ah, ws.agg16, s))) return rc;
+    int fused = 0;      // last layer without the energy head: edge MLP + coordinate head in one launch when it applies
+    if (last && ea.lig_only && (rc = launch_last_fused(ctx, ea, ws.emeta, Ah, ws.ring_flags, RING_FLAG_WORDS, (flags & DFM_LAST_FUSED) != 0, &fused, s))) return rc;
+    if (!fused && (rc = launch_edge_ws(ctx, ea, ws.emeta, Ah, ws.agg16, s))) return rc;
     if (prof) {
       CUDA_TRY(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], s));
       ctx->prof_used += 2;
     }
-    if (last && (rc = launch_node_coord(ctx, ea, s))) return rc;
+    if (last && !fused && (rc = launch_node_coord(ctx, ea, s))) return rc;
     if (last && !want_energy) break;   // layer-5 node update only feeds the energy head
     if ((rc = launch_node_z(ctx, l, M, ws.h16, ws.agg16, ws.z, s))) return rc;
     if ((rc = launch_graphnorm_stats(ctx, B, l, ws.z, ws.gscale, ws.gshift, s))) return rc;

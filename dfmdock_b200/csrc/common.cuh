@@ -159,6 +159,7 @@ struct dfm_ctx {
 };
 
 // Workspace carve-up for B trajectories (all offsets 256-byte aligned).
+constexpr int RING_FLAG_WORDS = 2048;
 struct Workspace {
   float* centre;     // [B,4]
   float* pos;        // [B,N,3,3] centred N/CA/C
@@ -182,6 +183,7 @@ struct Workspace {
   __half* agg16;     // [B,N,256] fp16(agg * 2^-6) written by edge_ws.cu
   float* gscale;     // [B,256] GraphNorm weight * rstd
   float* gshift;     // [B,256] GraphNorm bias - mean*mean_scale*gscale
+  unsigned int* ring_flags;   // [RING_FLAG_WORDS] ready / done counters of the fused last-layer kernel (last_ring.cuh)
   size_t bytes;
 };
 
@@ -222,6 +224,8 @@ struct EdgeArgs {
 };
 int launch_edge_simt(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s);
 int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, __half* agg16, cudaStream_t s);
+int launch_last_fused(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, unsigned int* ring_flags,
+                      int ring_flag_words, bool requested, int* used, cudaStream_t s);
 
 int launch_prepare(dfm_ctx* ctx, int B, const float* lig_pos, Workspace& ws, cudaStream_t s);
 int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const float* exp_noise, uint64_t seed,

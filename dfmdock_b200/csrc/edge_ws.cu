@@ -33,6 +33,8 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "last_ring.cuh"
+#include "coord_body.cuh"
 
 namespace ews {
 
@@ -76,7 +78,7 @@ constexpr int EPI_REGS = EWS_EPI_REGS;
 constexpr int MMA_REGS = EWS_MMA_REGS;
 static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEPI + 4) * 72, "register pool exceeded");
 #ifndef EWS_EXP
-#define EWS_EXP 0      // diagnostic experiments (wrong results): 1 = B rows from row 0, 2 = table rows from row 0, 4 = no tanh
+#define EWS_EXP 0      // diagnostic experiments (wrong results): 2 = table rows from row 0, 4 = no tanh, 8 = half of the B_j gathers, 16 = no spill stores
 #endif
 #ifndef EWS_TIMING
 #define EWS_TIMING 0   // 1: accumulate cycles spent in barrier waits per role into Params::timing (diagnostic builds)
@@ -283,10 +285,10 @@ __device__ __forceinline__ void lane_group_sum_h2(uint32_t* v, int lane) {
 
 // LAST: the last E_GCL layer (spill of the ligand rows' gated messages for the coordinate head, optional ligand-only tile walk);
 // a separate instantiation so that the five other launches carry neither its code nor its registers
-template <bool LAST>
-__global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_constant__ CUtensorMap tmB) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+// FUSED: the edge role of k_last_fused (LAST, ligand-only walk): the gated messages of a tile go to the ring of
+// last_ring.cuh instead of the spill buffer, `cta` is the rank among the ring.P producer CTAs
+template <bool LAST, bool FUSED>
+__device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tmB, const LastRing& ring, uint8_t* smem, const int cta) {
   const uint32_t sbase = smem_u32(smem);
   __half* vwr = reinterpret_cast<__half*>(smem + OFF_VEC) + 512;   // 16 * w1r
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 144);
@@ -297,7 +299,6 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
   const uint32_t bar_acce = sbase + OFF_BAR + 80;       // [2]
   const uint32_t bar_w = sbase + OFF_BAR + 128;         // weight image landed (bulk copy)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_trigger();            // the next kernel of the stream may start its prologue while this one drains (common.cuh)
 
   // ---- one-time setup (constants only: nothing a predecessor kernel wrote is read before pdl_wait) -----
   {
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
   pdl_wait();               // Ah / Bm / emeta of the preceding kernels are complete and visible from here on
   // contiguous tile ranges: concurrently running CTAs work on different trajectories, so the gathered B_j rows are
   // not hot lines shared by all SMs (strided assignment had every SM hammer the same 300 rows at the same time)
-  const int t_begin = (int)blockIdx.x * p.chunk;
+  const int t_begin = cta * p.chunk;
   const int t_end = min(p.ntiles, t_begin + p.chunk);
   // logical tile index -> tile of the [B*N/2] node-pair grid.  Ligand-only launches walk, per trajectory, the tiles
   // (b N + R) / 2 .. (b N + N - 1) / 2; when that count is one short of tpt (odd N) the last tile is simply done twice.
@@ -681,19 +682,44 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) m[k * 16 + j] = h2mul(m[k * 16 + j], gk[k]);
         }
-        if (node < p.total_nodes) {
+        if (FUSED) {
+          // hand the tile to the coordinate-head role through the L2-resident ring (last_ring.cuh); all 128 rows are
+          // written (rows of receptor residues and pad slots are ignored / zero-gated on the other side)
+          const unsigned sq = (unsigned)it * (unsigned)ring.P + (unsigned)cta;
+          const unsigned rs = sq % (unsigned)ring.NR, epoch = sq / (unsigned)ring.NR;
+          if (epoch > 0) {
+            if (lane == 0) ring_wait_ge(ring.done + rs, epoch);
+            __syncwarp();
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = q * 32 + rg + 8 * k;
+            __half* dst = ring.ring + ((size_t)rs * TILE_M + rr) * H + ch * 128 + cq * 16;
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 64 * v),
+                           "r"(m[k * 16 + 8 * v]), "r"(m[k * 16 + 8 * v + 1]), "r"(m[k * 16 + 8 * v + 2]), "r"(m[k * 16 + 8 * v + 3]),
+                           "r"(m[k * 16 + 8 * v + 4]), "r"(m[k * 16 + 8 * v + 5]), "r"(m[k * 16 + 8 * v + 6]), "r"(m[k * 16 + 8 * v + 7]) : "memory");
+          }
+          fence_proxy_async_all();            // these generic-proxy writes are read by TMA on the other side
+          __syncwarp();
+          if (lane == 0) { __threadfence(); red_release_gpu_add(ring.ready + rs, 1u); }
+          continue;
+        }
+        if (!(EWS_EXP & 16) && node < p.total_nodes) {
           const int b = node / p.N, i = node - b * p.N;
           if (i >= p.R) {
-            // spill in fragment order: this lane's 16 column pairs of row k are 64 contiguous bytes at position
-            // ch*128 + cq*32 of the row (the Wc1 image is K-permuted to match, node.cu k_image_pack_perm): two 256-bit
-            // stores per row instead of sixteen 32-bit ones.  All 64 slots are written -- the pad slots' gate is 0.
+            // spill in fragment order: this lane's column pairs 8 v .. 8 v + 7 of row k are 32 contiguous bytes at position
+            // ch*128 + v*64 + cq*16 of the row, so the four lanes of a row write one full 128-byte line per 256-bit store
+            // (the Wc1 image is K-permuted to match, node.cu k_image_pack_perm).  All 64 slots are written -- the pad
+            // slots' gate is 0.
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int slot = (q * 32 + rg + 8 * k) & 63;
-              __half* dst = p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + cq * 32;
+              __half* dst = p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + cq * 16;
 #pragma unroll
               for (int v = 0; v < 2; ++v)
-                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * v),
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 64 * v),
                              "r"(m[k * 16 + 8 * v]), "r"(m[k * 16 + 8 * v + 1]), "r"(m[k * 16 + 8 * v + 2]), "r"(m[k * 16 + 8 * v + 3]),
                              "r"(m[k * 16 + 8 * v + 4]), "r"(m[k * 16 + 8 * v + 5]), "r"(m[k * 16 + 8 * v + 6]), "r"(m[k * 16 + 8 * v + 7]) : "memory");
             }
@@ -729,6 +755,26 @@ __global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_
   if (warp == NPROD + NEPI) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(NT, 1) k_edge_ws(const Params p, const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();            // the next kernel of the stream may start its prologue while this one drains (common.cuh)
+  LastRing none{};
+  edge_body<LAST, false>(p, tmB, none, smem, (int)blockIdx.x);
+}
+
+// Last layer without the energy head, edge MLP + coordinate head in ONE launch: CTAs [0, ring.P) run the edge role over the
+// ligand residues' tiles, the others the coordinate head (coord_body.cuh) on the tiles the ring hands over.
+__global__ void __launch_bounds__(NT, 1) k_last_fused(const Params p, const __grid_constant__ CUtensorMap tmB, const ntc::Params pc,
+                                                      const __grid_constant__ CUtensorMap tmX, const LastRing ring) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();
+  if ((int)blockIdx.x < ring.P) edge_body<true, true>(p, tmB, ring, smem, (int)blockIdx.x);
+  else ntc::coord_body<true>(pc, tmX, ring, smem, (int)blockIdx.x - ring.P, (int)gridDim.x - ring.P);
 }
 
 }  // namespace ews
@@ -785,5 +831,77 @@ int launch_edge_ws(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __h
   if (p.last) CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<true>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p, tmB));
   else CUDA_TRY(dfm_launch_pdl(ews::k_edge_ws<false>, dim3(grid), dim3(ews::NT), ews::SMEM_ALLOC, s, p, tmB));
   LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// Last layer without the energy head as one launch (see k_last_fused / last_ring.cuh).  Returns DFM_OK with *used = 0 when the
+// fused form does not apply (not requested by flag or DFM_LAST_FUSED=1, small batches, a device that cannot hold the whole grid at once): the caller
+// then runs launch_edge_ws + launch_node_coord.
+int launch_last_fused(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const __half* Ahi, unsigned int* ring_flags,
+                      int ring_flag_words, bool requested, int* used, cudaStream_t s) {
+  *used = 0;
+  static int enabled = -1, split_pct = 0;
+  if (enabled < 0) {
+    const char* e = getenv("DFM_LAST_FUSED"); enabled = e ? atoi(e) : 0;
+    const char* f = getenv("DFM_LAST_FUSED_SPLIT"); split_pct = f ? atoi(f) : 68;     // % of the CTAs in the edge role
+  }
+  if (!(enabled || requested) || !a.last || !a.lig_only || a.N <= a.R || a.R <= 1) return 0;
+  const LayerW& w = ctx->layer[a.layer];
+  const int L = a.N - a.R;
+  ews::Params p{};
+  p.total_nodes = a.B * a.N;
+  p.N = a.N; p.R = a.R; p.K = a.K; p.last = 1; p.lig_only = 1;
+  {
+    const int L2a = ((a.N - 1) >> 1) - (a.R >> 1) + 1;
+    const int L2b = (a.N >> 1) - ((a.R + 1) >> 1) + 1;
+    p.tpt = (a.N & 1) ? (L2a > L2b ? L2a : L2b) : L2a;
+  }
+  p.ntiles = a.B * p.tpt;
+  const int grid = ctx->num_sms;
+  if (p.ntiles < 4 * grid) return 0;                       // too little work to split the SMs into two roles
+  int P = (grid * split_pct + 50) / 100;
+  if (P < 1) P = 1;
+  if (P > grid - 1) P = grid - 1;
+  p.chunk = (p.ntiles + P - 1) / P;
+  p.Wimg = w.img_W2h; p.emeta = emeta; p.Ahi = Ahi; p.Bm = reinterpret_cast<const __half*>(a.Bm);
+  p.Tdrp = w.Tdrp16h; p.Totp = w.Totp16h;
+  p.w1r = w.w1r; p.b2 = w.b2; p.wa = w.wa; p.ba = w.ba;
+  p.agg16 = nullptr; p.mstar = a.mstar;
+
+  LastRing ring{};
+  ring.P = P; ring.chunk = p.chunk; ring.ntiles = p.ntiles; ring.tpt = p.tpt; ring.N = a.N; ring.R = a.R;
+  ring.total_nodes = p.total_nodes;
+  // ring slots: four per producer, bounded by the spill buffer it lives in ([B, L, 64, 256] fp16) and by the flag words
+  const size_t spill_tiles = ((size_t)a.B * L * SLOTS) / ews::TILE_M;
+  size_t NR = (size_t)4 * P;
+  if (NR > spill_tiles) NR = spill_tiles;
+  if (NR > (size_t)ring_flag_words / 2) NR = (size_t)ring_flag_words / 2;
+  if (NR < 8) return 0;
+  ring.NR = (int)NR;
+  ring.ready = ring_flags; ring.done = ring_flags + NR;
+  ring.ring = a.mstar;
+
+  ntc::Params pc{};
+  pc.M = a.B * L * SLOTS; pc.ntiles = 0; pc.N = a.N; pc.R = a.R; pc.K = a.K;
+  pc.X = a.mstar; pc.W0 = w.img_Wc1s; pc.bias0 = w.bc1; pc.wc2 = w.wc2; pc.nbr = a.nbr; pc.pos = a.pos; pc.fbuf = a.fbuf;
+
+  static unsigned long long attr_devices = 0, ok_devices = 0;
+  constexpr int SMEM = (int)(ews::SMEM_ALLOC > ntc::SMEM_ALLOC ? ews::SMEM_ALLOC : ntc::SMEM_ALLOC);
+  if (dfm_once_per_device(attr_devices, ctx->device)) {
+    CUDA_TRY(cudaFuncSetAttribute(ews::k_last_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ews::k_last_fused, ews::NT, SMEM));
+    if (per_sm >= 1 && ctx->device < 64) ok_devices |= 1ull << ctx->device;      // the whole grid is co-resident
+  }
+  if (ctx->device >= 64 || !(ok_devices & (1ull << ctx->device))) return 0;
+
+  CUtensorMap tmB, tmX;
+  int rc = dfm_make_tmap_f16(&tmB, p.Bm, (uint64_t)p.total_nodes, H, 1);
+  if (rc) return rc;
+  if ((rc = dfm_make_tmap_f16(&tmX, ring.ring, (uint64_t)NR * ews::TILE_M, H, ntc::TILE_M))) return rc;
+  CUDA_TRY(cudaMemsetAsync(ring_flags, 0, sizeof(unsigned int) * 2 * NR, s));
+  CUDA_TRY(dfm_launch_pdl(ews::k_last_fused, dim3(grid), dim3(ews::NT), (size_t)SMEM, s, p, tmB, pc, tmX, ring));
+  LAUNCH_CHECK(ctx);
+  *used = 1;
   return 0;
 }

@@ -421,16 +421,29 @@ k_graph_sel(int B, int N, int R, int K, int knn, int ns, const float* __restrict
   }
 }
 
-template <int S>
-static int launch_graph_sel(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
-                            uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
-  constexpr int WARPS = 8;
+template <int WARPS, int S>
+static int launch_graph_sel_w(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
+                              uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
   const long rows = (long)B * ctx->N;
   const int grid = (int)((rows + WARPS - 1) / WARPS);
   k_graph_sel<WARPS, S><<<grid, WARPS * 32, 0, s>>>(B, ctx->N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, exp_noise,
                                                    seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
   LAUNCH_CHECK(ctx);
   return 0;
+}
+// rows (warps) per CTA of the pair scan; DFM_GRAPH_WARPS = 2 / 4 / 8 overrides the default for the pair-tile sweep of
+// BASELINE config #4 (profiles/c4_sweep.py -> profiles/r02/c4_pair_tile_sweep.txt)
+template <int S>
+static int launch_graph_sel(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
+                            uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
+  // default: 8 rows per CTA up to 16 keys per lane, 4 at 32 keys per lane (measured at 2x400 residues: 0.98 vs 1.22 ms,
+  // the 8-warp CTA of the 32-key instantiation is limited to one CTA per scheduler by its registers)
+  static int warps_env = -1;
+  if (warps_env < 0) { const char* e = getenv("DFM_GRAPH_WARPS"); warps_env = e ? atoi(e) : 0; }
+  const int warps = warps_env ? warps_env : (S >= 32 ? 4 : 8);
+  if (warps == 4) return launch_graph_sel_w<4, S>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
+  if (warps == 2) return launch_graph_sel_w<2, S>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
+  return launch_graph_sel_w<8, S>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
 }
 
 int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const float* exp_noise, uint64_t seed,

@@ -13,11 +13,12 @@ __global__ void k_image_pack(const float* __restrict__ W, int ldw, int col0, flo
   const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
   img[(((size_t)kb * 256 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(W[(size_t)n * ldw + col0 + k] * scale);
 }
-// Same image with K permuted into the edge epilogue's fragment order: position p = ch*128 + cq*32 + 2j + e holds column
-// c = ch*128 + 8j + 2cq + e (j = 0..15, cq = 0..3, e = 0..1) -- the order in which edge_ws.cu spills the gated messages.
+// Same image with K permuted into the order in which edge_ws.cu spills the gated messages: position
+// p = ch*128 + v*64 + cq*16 + 2 jl + e holds column c = ch*128 + 8 (8 v + jl) + 2 cq + e (v = 0..1, cq = 0..3, jl = 0..7,
+// e = 0..1): the eight registers of one 256-bit store are contiguous and the four lanes of a row write one full 128-byte line.
 __global__ void k_image_pack_perm(const float* __restrict__ W, int ldw, float scale, __half* __restrict__ img) {
   const int n = blockIdx.x, p = threadIdx.x;
-  const int q = p & 127, src = (p & 128) + 8 * ((q & 31) >> 1) + 2 * (q >> 5) + (q & 1);
+  const int q = p & 127, src = (p & 128) + 8 * (8 * (q >> 6) + ((q & 15) >> 1)) + 2 * ((q >> 4) & 3) + (q & 1);
   const int kb = p >> 6, c = (p & 63) >> 3, e = p & 7;
   img[(((size_t)kb * 256 + n) * 8 + (c ^ (n & 7))) * 8 + e] = __float2half_rn(W[(size_t)n * ldw + src] * scale);
 }

@@ -52,6 +52,7 @@ class Score_Model:
         self.pos_width = int(self.state_dict_cpu["positional_embed.weight"].shape[1])
         self.precision = precision          # "fp16" (tcgen05, default) or "fp32" (FFMA parity mode)
         self.graph_generic = False          # True: always build the graph with the generic kernel (the N > 1024 path)
+        self.last_fused = False             # True: last layer + coordinate head as one launch (DFM_LAST_FUSED, test knob)
         self.edge_rng = "torch"             # forward(batch): "torch" = reference-style global RNG, "philox" = in-kernel
         self.device = None
         self._ctx = None
@@ -194,6 +195,8 @@ class Score_Model:
             f |= _lib.ODE
         if kw.get("graph_generic") or self.graph_generic:
             f |= _lib.GRAPH_GENERIC
+        if kw.get("last_fused") or self.last_fused:
+            f |= _lib.LAST_FUSED
         return f
 
     # ---- batched operators ---------------------------------------------------------------------------

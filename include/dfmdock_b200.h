@@ -53,8 +53,12 @@ enum {
   DFM_NOISE_ANNEAL = 1u << 3,  /* noise_scale = t (inference_base.py:428-430) */
   DFM_CENTRE_ALL_ATOMS = 1u << 4, /* rotate about the N/CA/C centroid (inference.py:224-245) instead of the CA centroid (inference_base.py:322-343) */
   DFM_ODE = 1u << 5,           /* probability-flow ODE branch of torch_reverse (so3_diffuser.py:366-367) */
-  DFM_GRAPH_GENERIC = 1u << 6  /* build the stochastic graph with the generic (shared-memory) kernel that complexes of more than
+  DFM_GRAPH_GENERIC = 1u << 6, /* build the stochastic graph with the generic (shared-memory) kernel that complexes of more than
                                   1024 residues use, whatever the size: same neighbours as the register-resident kernels (test knob) */
+  DFM_LAST_FUSED = 1u << 7     /* last layer without the energy head as ONE launch: the SMs are split into an edge-MLP role and a
+                                  coordinate-head role, the gated messages travel through an L2-resident ring instead of HBM
+                                  (same results bit for bit; measured slower than the two-kernel form on B200, so it is off by
+                                  default -- DESIGN.md section 6; the environment variable DFM_LAST_FUSED=1 turns it on globally) */
 };
 
 /* Fixed architecture of the shipped checkpoints (configs/model/score_model_mlsb.yaml). */

@@ -260,3 +260,36 @@ def test_batched_sampler_uses_the_checkpoints_own_sigmas():
             assert torch.equal(a[k], b[k]), (tag, k)
         outs[tag] = a
     assert not torch.equal(outs["default"]["tr_update"], outs["custom"]["tr_update"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_rec,n_lig,B", [(150, 150, 64), (151, 148, 48), (120, 97, 96)])
+def test_last_layer_fused_launch_is_bit_identical(n_rec, n_lig, B):
+    """DFM_LAST_FUSED: the last layer's edge MLP and the coordinate head (src/models/egnn.py:118-148) as one launch, tiles of
+    gated messages handed from an edge role to a coordinate-head role through an L2-resident ring (csrc/last_ring.cuh).  Same
+    arithmetic on the same rows in the same order as the two-kernel form -> forces and scores equal bit for bit; even / odd
+    receptor and ligand sizes cover the tiles that straddle the chains and the duplicated last tile of an odd complex."""
+    import torch
+    from dfmdock_b200 import Score_Model
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd, hp = synthetic_state_dict(1, 66), synthetic_hparams(66)
+    batch = synthetic_complex(n_rec, n_lig, seed=5)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([15.0, 0.0, 0.0])
+    model = Score_Model(sd, hp, precision="fp16").to("cuda")
+    model.set_complex(batch)
+    g = torch.Generator().manual_seed(0)
+    lig = (batch["lig_pos"][None] + torch.randn(B, 1, 1, 3, generator=g)).contiguous()
+    t = torch.full((B,), 0.35)
+    a = model.score(lig, t, seed=11, stream_base=3, forward_index=2)
+    before = model.launch_count
+    model.last_fused = True
+    b = model.score(lig, t, seed=11, stream_base=3, forward_index=2)
+    fused_launches = model.launch_count - before
+    model.last_fused = False
+    c = model.score(lig, t, seed=11, stream_base=3, forward_index=2)
+    unfused_launches = model.launch_count - before - fused_launches
+    assert fused_launches == unfused_launches - 1, (fused_launches, unfused_launches)      # the fused form really ran
+    for k in ("f", "tr_score", "rot_score"):
+        assert torch.equal(a[k], c[k]), k
+        assert torch.equal(a[k], b[k]), (k, float((a[k] - b[k]).abs().max()))
