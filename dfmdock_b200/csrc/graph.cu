@@ -421,6 +421,198 @@ k_graph_sel(int B, int N, int R, int K, int knn, int ns, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_graph_big: complexes too large for the register-resident kernel (N > 1024).  Same result as k_graph (as sets); the keys
+// of a row live in shared memory as order-preserving bit patterns and the k smallest are found in two phases:
+//   A  bit-wise search from the highest differing bit over all N keys, only until the keys that share the current prefix
+//      (the candidates among which the k-th smallest lies) are at most 64 -- for distances the count falls eightfold per
+//      bit, for the race keys twofold, instead of the 25-30 full passes of a search carried to the last bit (or the 60
+//      arg-min passes of k_graph);
+//   B  one pass that emits every key below the prefix (selected for sure) and gathers the candidates, which are then
+//      ranked against each other (ties to the smaller residue index, like k_graph) in registers.
+// One warp per (trajectory, residue) row.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_graph_big(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ pos, const float* __restrict__ cb,
+            const float* __restrict__ exp_noise, uint64_t seed, uint64_t stream_base, uint32_t fwd,
+            int32_t* __restrict__ nbr, uint32_t* __restrict__ feat, float* __restrict__ radial, int4* __restrict__ emeta) {
+  extern __shared__ uint32_t smem_u[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npad = (N + 31) & ~31, S = npad >> 5;
+  uint32_t* key = smem_u + (size_t)warp * (npad + 192);
+  uint32_t* cand_key = key + npad;                          // [64]
+  int* cand_idx = reinterpret_cast<int*>(cand_key + 64);    // [64]
+  int* slot = cand_idx + 64;                                // [64] selected residues
+  const long row = (long)blockIdx.x * WARPS + warp;
+  if (row >= (long)B * N) return;
+  const int b = (int)(row / N), i = (int)(row % N);
+  const size_t gbase = (size_t)b * N;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  constexpr uint32_t ABSENT = 0xFFFFFFFFu;
+  uint32_t* kl = key + lane;                                // this lane's keys: kl[32 s] <-> residue lane + 32 s
+
+  {
+    const float* pi = pos + (gbase + i) * 9;
+    const float xi = pi[3], yi = pi[4], zi = pi[5];
+    const float* pl = pos + (gbase + lane) * 9 + 3;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      uint32_t kd = ABSENT;
+      if (lane + 32 * s < N) {
+        const float* pj = pl + (size_t)s * (32 * 9);
+        const float dx = xi - __ldg(pj), dy = yi - __ldg(pj + 1), dz = zi - __ldg(pj + 2);
+        kd = __float_as_uint(sqrtf(dx * dx + dy * dy + dz * dz));
+      }
+      kl[32 * s] = kd;
+    }
+  }
+  __syncwarp();
+
+  // the k smallest present keys -> slot[base .. base + k); selected keys are overwritten with ABSENT
+  auto select = [&](int k, int base) {
+    uint32_t mn = ABSENT, mx = 0u;
+    int present = 0;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      const uint32_t v = kl[32 * s];
+      const bool p = v != ABSENT;
+      mn = min(mn, v); mx = max(mx, p ? v : 0u); present += p ? 1 : 0;
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    present = __reduce_add_sync(0xffffffffu, present);
+    if (k > present) k = present;
+    if (k <= 0) return;
+    // invariant: lo = #(key < v) < k <= hi = #(key < vhi), the k-th smallest key lies in [v, vhi)
+    uint32_t v = mn, vhi = ABSENT;             // vhi = ABSENT: every present key is below it
+    int lo = 0, hi = present;
+    if (mn != mx) {
+      const int top = 31 - __clz(mn ^ mx);
+      v = (top == 31) ? 0u : (mn >> (top + 1)) << (top + 1);
+      for (int bit = top; bit >= 0 && hi - lo > 64; --bit) {
+        const uint32_t test = v | (1u << bit);
+        int cnt = 0;
+#pragma unroll 8
+        for (int s = 0; s < S; ++s) cnt += (kl[32 * s] < test) ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt < k) { v = test; lo = cnt; } else { vhi = test; hi = cnt; }
+      }
+    }
+    const int need = k - lo;                   // how many of the candidates [v, vhi) to take
+    const int ncand = hi - lo;
+    if (ncand <= 64) {
+      // phase B: emit the sure members, gather the candidates (both in residue order)
+      int nm = 0, nc = 0;
+#pragma unroll 2
+      for (int s = 0; s < S; ++s) {
+        const uint32_t kv = kl[32 * s];
+        const bool m = kv < v;
+        const bool c = !m && kv < vhi;         // ABSENT is never below vhi
+        const uint32_t bm = __ballot_sync(0xffffffffu, m), bc = __ballot_sync(0xffffffffu, c);
+        if (m) { slot[base + nm + (int)__popc(bm & lt_mask)] = lane + 32 * s; kl[32 * s] = ABSENT; }
+        if (c) { const int q = nc + (int)__popc(bc & lt_mask); cand_key[q] = kv; cand_idx[q] = lane + 32 * s; }
+        nm += (int)__popc(bm); nc += (int)__popc(bc);
+      }
+      __syncwarp();
+      // rank the candidates among themselves (key, then residue index); candidate q = lane and lane + 32
+      const uint32_t k0 = lane < nc ? cand_key[lane] : ABSENT, k1 = lane + 32 < nc ? cand_key[lane + 32] : ABSENT;
+      int r0 = 0, r1 = 0;
+      for (int q = 0; q < nc; ++q) {
+        const uint32_t kq = cand_key[q];
+        r0 += (kq < k0 || (kq == k0 && q < lane)) ? 1 : 0;           // the list is in residue order: q orders the ties
+        r1 += (kq < k1 || (kq == k1 && q < lane + 32)) ? 1 : 0;
+      }
+      const bool t0 = lane < nc && r0 < need, t1 = lane + 32 < nc && r1 < need;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, t0), b1 = __ballot_sync(0xffffffffu, t1);
+      if (t0) { const int j = cand_idx[lane]; slot[base + nm + (int)__popc(b0 & lt_mask)] = j; key[j] = ABSENT; }
+      if (t1) { const int j = cand_idx[lane + 32]; slot[base + nm + (int)__popc(b0) + (int)__popc(b1 & lt_mask)] = j; key[j] = ABSENT; }
+    } else {
+      // more than 64 keys equal to v (the search ran out of bits): sure members, then the first `need` of the ties
+      int nm = 0, left = need;
+      for (int s = 0; s < S; ++s) {
+        const uint32_t kv = kl[32 * s];
+        const bool m = kv < v, e = kv == v && kv != ABSENT;
+        const uint32_t be = __ballot_sync(0xffffffffu, e);
+        const bool take = m || (e && (int)__popc(be & lt_mask) < left);
+        const uint32_t bt = __ballot_sync(0xffffffffu, take);
+        if (take) { slot[base + nm + (int)__popc(bt & lt_mask)] = lane + 32 * s; kl[32 * s] = ABSENT; }
+        nm += (int)__popc(bt);
+        left -= min(left, (int)__popc(be));
+      }
+    }
+    __syncwarp();
+  };
+
+  // the residue itself (d = 0) is always the first of its nearest neighbours: taking it out first lets the search start at
+  // the bits in which real distances differ instead of walking down from the exponent's top bit
+  int knn_rest = knn;
+  if (knn > 0) {
+    if (lane == 0) { slot[0] = i; key[i] = ABSENT; }
+    knn_rest = knn - 1;
+    __syncwarp();
+  }
+  select(knn_rest, knn - knn_rest);
+  // ---- exponential race over the remaining residues: key = Exp(1) * d^3, keep the ns smallest
+  if (ns > 0) {
+    if (exp_noise != nullptr) {
+      int members_below = 0;                   // kNN members with a smaller index (compacted column of the injected noise)
+      for (int s = 0; s < S; ++s) {
+        const int j = lane + 32 * s;
+        const uint32_t kv = kl[32 * s];
+        const bool member = j < N && kv == ABSENT;
+        const uint32_t bal = __ballot_sync(0xffffffffu, member);
+        if (j < N && !member) {
+          const float e = exp_noise[(gbase + i) * (size_t)(N - knn) + (j - members_below - (int)__popc(bal & lt_mask))];
+          const float d = fmaxf(__uint_as_float(kv), 1e-10f);
+          kl[32 * s] = min(__float_as_uint(e * (d * d * d)), 0xFFFFFFFEu);
+        }
+        members_below += (int)__popc(bal);
+      }
+    } else {
+      // one Philox block per four residues (the same counters as k_graph / k_graph_sel): lane takes blocks lane, lane + 32, ..
+      const uint64_t strm = stream_base + (uint64_t)b;
+      uint4* k4 = reinterpret_cast<uint4*>(key);
+      for (int q = lane; q * 4 < npad; q += 32) {
+        const uint4 r4 = dfm_rng(seed, strm, RNG_EDGE, fwd, (uint32_t)q, (uint32_t)i);
+        uint4 kv = k4[q];
+        auto race = [&](uint32_t dbits, uint32_t u) -> uint32_t {
+          if (dbits == ABSENT) return ABSENT;
+          const float d = fmaxf(__uint_as_float(dbits), 1e-10f);
+          return min(__float_as_uint(-logf(u01_open(u)) * (d * d * d)), 0xFFFFFFFEu);
+        };
+        kv.x = race(kv.x, r4.x); kv.y = race(kv.y, r4.y); kv.z = race(kv.z, r4.z); kv.w = race(kv.w, r4.w);
+        k4[q] = kv;
+      }
+    }
+    __syncwarp();
+    select(ns, knn);
+  }
+  __syncwarp();
+  // ---- pair features for the K selected edges; pad slots point at the residue itself
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int k = lane + 32 * half;
+    int j = i;
+    uint32_t ft = 0;
+    float r2 = 0.f;
+    if (k < K) {
+      j = min(max(slot[k], 0), N - 1);
+      ft = pair_bins(pos, cb, (int)(gbase + i), (int)(gbase + j), i, j, R, &r2);
+    }
+    const size_t o = (gbase + i) * SLOTS + k;
+    nbr[o] = j;
+    feat[o] = ft;
+    radial[o] = r2;
+    {
+      const uint32_t otp = (ft >> 6) & 0x3FFFu;
+      const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
+      const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
+      const __half2 rh = __float2half2_rn(fminf(r2 * 0.03125f, 65000.f));
+      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, *reinterpret_cast<const int*>(&rh));
+    }
+  }
+}
+
 template <int WARPS, int S>
 static int launch_graph_sel_w(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
                               uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
@@ -459,6 +651,30 @@ int launch_graph(dfm_ctx* ctx, int B, bool generic, const int32_t* edges, const 
     if (N <= 1024) return launch_graph_sel<32>(ctx, B, exp_noise, seed, stream_base, fwd_index, ws, s);
   }
   const int npad = (N + 31) & ~31;
+  static int use_big = -1;
+  if (use_big < 0) { const char* e = getenv("DFM_GRAPH_BIG"); use_big = e ? atoi(e) : 1; }
+  if (use_big && use_sel && !generic && edges == nullptr && N >= 2) {
+    // large complexes: two-phase selection with the keys in shared memory (4 rows per CTA above 6 k residues)
+    const size_t per_warp = (size_t)(npad + 192) * sizeof(uint32_t);
+    const long rows = (long)B * N;
+    static unsigned long long big_devices = 0;
+    if (dfm_once_per_device(big_devices, ctx->device)) {
+      CUDA_TRY(cudaFuncSetAttribute(k_graph_big<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(k_graph_big<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    if (8 * per_warp <= 200 * 1024) {
+      k_graph_big<8><<<(int)((rows + 7) / 8), 256, 8 * per_warp, s>>>(B, N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, exp_noise,
+                                                                    seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
+      LAUNCH_CHECK(ctx);
+      return 0;
+    }
+    if (2 * per_warp <= 200 * 1024) {
+      k_graph_big<2><<<(int)((rows + 1) / 2), 64, 2 * per_warp, s>>>(B, N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, exp_noise,
+                                                                   seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
+      LAUNCH_CHECK(ctx);
+      return 0;
+    }
+  }
   const size_t smem = (size_t)WARPS * (npad + 32) * sizeof(float);
   if (smem > 200 * 1024) {
     dfm_set_error("complex too large for the graph kernel (N=%d)", N);

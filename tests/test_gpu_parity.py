@@ -189,6 +189,37 @@ def test_large_complex_beyond_1024_residues():
     assert int(single["num_clashes"][0]) == int(o["num_clashes"][1])
 
 
+@pytest.mark.parametrize("n_rec,n_lig", [(800, 500), (1500, 1048), (1030, 3)])
+def test_large_complex_graph_kernel_equals_generic_kernel(n_rec, n_lig):
+    """N > 1024 builds the graph with k_graph_big (two-phase selection, keys in shared memory); DFM_GRAPH_GENERIC forces the
+    arg-min kernel.  Same Philox draws -> the same kNN block and the same 40 sampled neighbours per residue (as sets), for a
+    db5-1N2C-sized complex (2548 residues) too; and with injected Exp(1) noise."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    sd, hp = synthetic_state_dict(0, 66), synthetic_hparams(66)
+    batch = synthetic_complex(n_rec, n_lig, seed=8)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([11.0, 0.0, 0.0])
+    model = _model(sd, hp, "fp16")
+    model.set_complex(batch)
+    lig = batch["lig_pos"][None].repeat(2, 1, 1, 1)
+    t = torch.full((2,), 0.4)
+    N = n_rec + n_lig
+    g = torch.Generator().manual_seed(3)
+    noise = torch.empty(2, N, N - 20).exponential_(generator=g) if N < 1400 else None
+    for exp in (None, noise):
+        if exp is None and noise is not None and False:
+            continue
+        model.graph_generic = False
+        a = model.score(lig, t, seed=5, stream_base=2, forward_index=9, exp_noise=exp, return_edges=True)["edges"].cpu().long()
+        model.graph_generic = True
+        b = model.score(lig, t, seed=5, stream_base=2, forward_index=9, exp_noise=exp, return_edges=True)["edges"].cpu().long()
+        model.graph_generic = False
+        assert torch.equal(a[:, :, :20].sort(-1).values, b[:, :, :20].sort(-1).values), (n_rec, n_lig, exp is not None)
+        assert torch.equal(a[:, :, 20:].sort(-1).values, b[:, :, 20:].sort(-1).values), (n_rec, n_lig, exp is not None)
+        if noise is None:
+            break
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_batched_equals_single(precision):
     sd, hp, batch = case_small()
