@@ -7,8 +7,8 @@
 //   warps 0-15  producers: table rows of every edge gathered into registers one K block ahead (L2), + A_i + the B_j row
 //               the loaders staged + radial * w1r, SiLU via tanh.approx.f16x2 in packed half2, written in place into
 //               the 128 x 256 fp16 operand tile S (SWIZZLE_128B, K-major), one 64-column K block at a time
-//   warps 25-26 loaders: cp.async the B_j rows of a K block straight into the S tile as soon as the previous tile's MMA
-//               has consumed that block
+//   warps 25-26 loaders: TMA tile::gather4 of the B_j rows of a K block straight into the S tile as soon as the previous
+//               tile's MMA has consumed that block; warp 27 relays the completion to the producers (EWS_RELAY)
 //   warp  24    MMA issuer: one K = 16 MMA that sets the accumulator to b2/2 (constant 1/16 tile x bias tile, no-swizzle
 //               descriptors), then D[128 x 256] (TMEM, fp32) += S * (W2/2)^T: four tcgen05.mma per K block, one
 //               tcgen05.commit per K block (frees it for the next tile) and one per tile (accumulator ready)
@@ -53,7 +53,7 @@ constexpr uint32_t OFF_VEC32 = OFF_META + 16 * 2 * 8 * 16; // fragment-ordered b
 constexpr uint32_t OFF_BAR = OFF_VEC32 + 2048;            // 16 mbarriers + tmem base
 // b2 folded into the accumulator by one extra K = 16 MMA per tile: A = [128 x 16] of 1/16, B = [256 x 16] with row n = b2[n]/2
 // (both K-major, no swizzle: 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row groups 256 B apart)
-constexpr uint32_t OFF_BIASA = (OFF_BAR + 160 + 127) & ~127u;
+constexpr uint32_t OFF_BIASA = (OFF_BAR + 192 + 127) & ~127u;
 constexpr uint32_t OFF_BIASB = OFF_BIASA + 128 * 32;
 constexpr uint32_t SMEM_BYTES = OFF_BIASB + 256 * 32;
 static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
@@ -108,8 +108,12 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_LOAD_BYKB
 #define EWS_LOAD_BYKB 0    // 1: loader warp lw takes whole K blocks lw, lw + EWS_NLOAD, ..; 0: every loader warp takes a share of the rows of every K block
 #endif
+#ifndef EWS_RELAY
+#define EWS_RELAY 1        // 1: two loader warps issue the gathers, the third waits for their transaction bytes and hands every K block to
+#endif                     // the 16 producer warps through a one-arrival barrier (the producers then wake once per K block instead of at
+                           // every partial completion of the 32 gathers)
 #ifndef EWS_NLOAD
-#define EWS_NLOAD 3        // B_j loader warps (1..3): the 32 gather units of a K block are split over them
+#define EWS_NLOAD (EWS_RELAY ? 2 : 3)   // B_j loader warps that issue gathers: the 32 gather units of a K block are split over them
 #endif
 #ifndef EWS_BULK_W
 #define EWS_BULK_W 1      // weight image by cp.async.bulk (TMA 1-D), overlapped with the rest of the set-up and the first tile's build
@@ -298,6 +302,7 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
   const uint32_t bar_accf = sbase + OFF_BAR + 64;       // [2]
   const uint32_t bar_acce = sbase + OFF_BAR + 80;       // [2]
   const uint32_t bar_w = sbase + OFF_BAR + 128;         // weight image landed (bulk copy)
+  const uint32_t bar_bready = sbase + OFF_BAR + 160;    // [4] EWS_RELAY: one arrival per K block once all its B_j rows have landed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup (constants only: nothing a predecessor kernel wrote is read before pdl_wait) -----
@@ -337,7 +342,7 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_bfull + 8 * i, EWS_LOAD_BYKB ? 1 : EWS_NLOAD);
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_bfull + 8 * i, EWS_LOAD_BYKB ? 1 : EWS_NLOAD); mbar_init(bar_bready + 8 * i, 1); }
     tma_prefetch_desc(&tmB);
 #if EWS_BULK_W
     mbar_init(bar_w, 1);
@@ -472,24 +477,24 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
       const uint32_t par = (uint32_t)(it & 1);
       // kb 0 (buffer 0); prefetch kb 1
       issue(g1, mcur, ao, 1);
-      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 96u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 160u : 96u), par));
       compute(g0, mcur, 0);
       fence_async_smem(); mbar_arrive(pbar + 0u);
       // kb 1 (buffer 1); prefetch kb 2
       issue(g0, mcur, ao, 2);
-      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 104u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 168u : 104u), par));
       compute(g1, mcur, 1);
       fence_async_smem(); mbar_arrive(pbar + 8u);
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
-      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 112u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 176u : 112u), par));
       compute(g0, mcur, 2);
       fence_async_smem(); mbar_arrive(pbar + 16u);
       // kb 3 (buffer 1); stage the next tile's metadata (its load has had three K blocks to land), prefetch its kb 0
       if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
       __syncwarp();
       if (has_next) issue(g0, mnext, aon, 0);
-      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + 120u, par));
+      TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 184u : 120u), par));
       compute(g1, mcur, 3);
       fence_async_smem(); mbar_arrive(pbar + 24u);
     }
@@ -576,6 +581,20 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
       }
       if (EWS_TIMING && lw == 0 && lane == 0) { atomicAdd(p.timing + 2, tw0); atomicAdd(p.timing + 3, (unsigned long long)(clock64() - tstart)); }
     }
+#if EWS_RELAY
+    else if (warp == NPROD + NEPI + EWS_NLOAD + 1) {
+      // relay: bar_bfull completes by transaction bytes, and every partial completion wakes the threads parked on it; this
+      // warp absorbs those wake-ups and arrives once on bar_bready, the barrier the 512 producer threads wait on
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait<0>(bar_bfull + 8 * kb, (uint32_t)(it & 1));
+          if (lane == 0) mbar_arrive(bar_bready + 8 * kb);
+        }
+      }
+    }
+#endif
     __syncwarp();
   } else {
     // =================================== EPILOGUE =====================================================
