@@ -54,7 +54,7 @@ Workspace carve_workspace(const dfm_ctx* ctx, int B, void* base) {
   w.z = (float*)take(b * N * H * 4);
   w.y = (float*)take(b * N * H * 4);
   w.gstat = (float*)take(b * 2 * H * 4);
-  w.mstar = (__half*)take(b * L * SLOTS * H * 2);
+  w.mstar = (__half*)take(((b * L + 1) & ~(size_t)1) * SLOTS * H * 2);   // whole 128-row tiles (two ligand residues each)
   w.fbuf = (float*)take(b * L * 4 * 4);
   w.esum = (float*)take(b * R * 4 * 4);
   w.tsc = (float*)take(b * 8 * 4);

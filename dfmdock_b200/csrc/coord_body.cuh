@@ -215,7 +215,7 @@ __device__ __forceinline__ void coord_body(const Params& p, const CUtensorMap& t
           const uint32_t slot = c % NSLOT;
           if (c >= (uint32_t)NSLOT) mbar_wait(bar_empty + 8 * slot, ((c / NSLOT) - 1) & 1u);
           mbar_expect_tx(bar_full + 8 * slot, S_KBLK);
-          tma_load_2d(sbase + OFF_S + slot * S_KBLK, &tmX, kb * 64, row0, bar_full + 8 * slot);
+          tma_load_2d(sbase + OFF_S + slot * S_KBLK, &tmX, 0, row0 * 4 + kb * TILE_M, bar_full + 8 * slot);   // [tile][K block][128][64]
         }
       }
     }

@@ -713,10 +713,10 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int rr = q * 32 + rg + 8 * k;
-            __half* dst = ring.ring + ((size_t)rs * TILE_M + rr) * H + ch * 128 + cq * 16;
+            __half* dst = ring.ring + (((size_t)rs * 4 + ch * 2) * TILE_M + rr) * 64 + cq * 16;      // [slot][K block][row][64]
 #pragma unroll
             for (int v = 0; v < 2; ++v)
-              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 64 * v),
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + (size_t)v * (TILE_M * 64)),
                            "r"(m[k * 16 + 8 * v]), "r"(m[k * 16 + 8 * v + 1]), "r"(m[k * 16 + 8 * v + 2]), "r"(m[k * 16 + 8 * v + 3]),
                            "r"(m[k * 16 + 8 * v + 4]), "r"(m[k * 16 + 8 * v + 5]), "r"(m[k * 16 + 8 * v + 6]), "r"(m[k * 16 + 8 * v + 7]) : "memory");
           }
@@ -728,17 +728,19 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
         if (!(EWS_EXP & 16) && node < p.total_nodes) {
           const int b = node / p.N, i = node - b * p.N;
           if (i >= p.R) {
-            // spill in fragment order: this lane's column pairs 8 v .. 8 v + 7 of row k are 32 contiguous bytes at position
-            // ch*128 + v*64 + cq*16 of the row, so the four lanes of a row write one full 128-byte line per 256-bit store
-            // (the Wc1 image is K-permuted to match, node.cu k_image_pack_perm).  All 64 slots are written -- the pad
-            // slots' gate is 0.
+            // spill in fragment order and K-block-major per tile: [tile][K block ch*2+v][tile row][64], this lane's column
+            // pairs 8 v .. 8 v + 7 of row k are the 32 contiguous bytes at position cq*16 of the row's K block, so the four
+            // lanes of a row write one full 128-byte line per 256-bit store and the coordinate head fetches a K block of
+            // a tile as ONE contiguous 16 KB box (the Wc1 image is K-permuted to match, node.cu k_image_pack_perm).  All
+            // 64 slots are written -- the pad slots' gate is 0.
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int slot = (q * 32 + rg + 8 * k) & 63;
-              __half* dst = p.mstar + (((size_t)b * (p.N - p.R) + (i - p.R)) * SLOTS + slot) * H + ch * 128 + cq * 16;
+              const size_t ln = (size_t)b * (p.N - p.R) + (i - p.R);          // ligand residue -> tile ln / 2, tile row (ln & 1) * 64 + slot
+              __half* dst = p.mstar + ((((ln >> 1) * 4 + ch * 2) * TILE_M) + (ln & 1) * 64 + slot) * 64 + cq * 16;
 #pragma unroll
               for (int v = 0; v < 2; ++v)
-                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 64 * v),
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + (size_t)v * (TILE_M * 64)),
                              "r"(m[k * 16 + 8 * v]), "r"(m[k * 16 + 8 * v + 1]), "r"(m[k * 16 + 8 * v + 2]), "r"(m[k * 16 + 8 * v + 3]),
                              "r"(m[k * 16 + 8 * v + 4]), "r"(m[k * 16 + 8 * v + 5]), "r"(m[k * 16 + 8 * v + 6]), "r"(m[k * 16 + 8 * v + 7]) : "memory");
             }
@@ -917,7 +919,7 @@ int launch_last_fused(dfm_ctx* ctx, const EdgeArgs& a, const int4* emeta, const 
   CUtensorMap tmB, tmX;
   int rc = dfm_make_tmap_f16(&tmB, p.Bm, (uint64_t)p.total_nodes, H, 1);
   if (rc) return rc;
-  if ((rc = dfm_make_tmap_f16(&tmX, ring.ring, (uint64_t)NR * ews::TILE_M, H, ntc::TILE_M))) return rc;
+  if ((rc = dfm_make_tmap_f16(&tmX, ring.ring, (uint64_t)NR * 4 * ews::TILE_M, 64, ntc::TILE_M))) return rc;
   CUDA_TRY(cudaMemsetAsync(ring_flags, 0, sizeof(unsigned int) * 2 * NR, s));
   CUDA_TRY(dfm_launch_pdl(ews::k_last_fused, dim3(grid), dim3(ews::NT), (size_t)SMEM, s, p, tmB, pc, tmX, ring));
   LAUNCH_CHECK(ctx);

@@ -1,6 +1,6 @@
 // Coordinate head of the last E_GCL layer on the tensor cores (ligand rows only):
 //   w = clamp(wc2 . SiLU(Wc1 m* + bc1), +-2),  f_i = mean_k (x_i - x_j) / (|x_i - x_j| + 1) w      (src/models/egnn.py:118-148)
-// m* = the gated messages edge_ws.cu spills for the ligand residues, [B*L, 64 slots, 256] fp16 (x 2^-6).
+// m* = the gated messages edge_ws.cu spills for the ligand residues, fp16 (x 2^-6), [tile = 2 residues][4 K blocks][128 rows][64].
 //
 // The spill is stored with the columns of each 128-column half in the epilogue's fragment order (edge_ws.cu, position
 // cq*32 + 2j + e <-> column 8j + 2cq + e, so that a thread stores 64 contiguous bytes); the image of Wc1 carries the same
@@ -32,7 +32,8 @@ static int launch(dfm_ctx* ctx, const Params& p, int grid, cudaStream_t s) {
   }
   if (grid <= 0) return 0;
   CUtensorMap tmX;
-  int rc = dfm_make_tmap_f16(&tmX, p.X, (uint64_t)p.M, H, TILE_M);
+  // the spill as [tiles * 4 K blocks * 128 rows, 64 columns]: one K block of a tile is one contiguous 16 KB box
+  int rc = dfm_make_tmap_f16(&tmX, p.X, (uint64_t)p.ntiles * 4 * TILE_M, 64, TILE_M);
   if (rc) return rc;
   CUDA_TRY(dfm_launch_pdl(k_coord, dim3(grid), dim3(NT), SMEM_ALLOC, s, p, tmX));
   LAUNCH_CHECK(ctx);
@@ -63,6 +64,10 @@ int launch_node_coord(dfm_ctx* ctx, const EdgeArgs& a, cudaStream_t s) {
   ntc::Params p{};
   const int L = a.N - a.R;
   p.M = a.B * L * SLOTS; p.ntiles = (a.B * L + 1) / 2; p.N = a.N; p.R = a.R; p.K = a.K;
+  if ((a.B * L) & 1) {      // odd number of ligand residues in the batch: the second half of the last tile is never written
+    for (int kb = 0; kb < 4; ++kb)
+      CUDA_TRY(cudaMemsetAsync(a.mstar + (((size_t)(p.ntiles - 1) * 4 + kb) * 128 + 64) * 64, 0, 64 * 64 * sizeof(__half), s));
+  }
   p.X = a.mstar; p.W0 = w.img_Wc1s; p.bias0 = w.bc1; p.wc2 = w.wc2; p.nbr = a.nbr; p.pos = a.pos; p.fbuf = a.fbuf;
   return ntc::launch(ctx, p, p.ntiles < ctx->num_sms ? p.ntiles : ctx->num_sms, s);
 }
