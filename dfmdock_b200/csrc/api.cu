@@ -113,6 +113,7 @@ extern "C" void dfm_destroy(dfm_ctx* ctx) {
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaFree(ctx->h0);
   cudaFree(ctx->rec_pos);
+  cudaFree(ctx->clash_partial);
   delete ctx;
 }
 
@@ -288,6 +289,15 @@ extern "C" int dfm_set_complex(dfm_ctx* ctx, int R, int L, int x_dim, const floa
     ctx->rec_pos = nullptr; ctx->rec_cap = 0;
     CUDA_TRY(cudaMalloc(&ctx->rec_pos, sizeof(float) * cap));
     ctx->rec_cap = cap;
+  }
+  if (clash_scratch_floats(R, L) > ctx->clash_cap) {
+    size_t cap = ctx->clash_cap ? ctx->clash_cap : clash_scratch_floats(256, 256);
+    while (cap < clash_scratch_floats(R, L)) cap *= 2;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(ctx->clash_partial);
+    ctx->clash_partial = nullptr; ctx->clash_cap = 0;
+    CUDA_TRY(cudaMalloc(&ctx->clash_partial, sizeof(float) * cap));
+    ctx->clash_cap = cap;
   }
   CUDA_TRY(cudaMemcpyAsync(ctx->rec_pos, rec_pos, sizeof(float) * (size_t)R * 9, cudaMemcpyDeviceToDevice, s));
   int rc = launch_single_embed(ctx, rec_x, lig_x, s);

@@ -149,6 +149,8 @@ struct dfm_ctx {
   float* h0 = nullptr;        // [N,256]
   float* rec_pos = nullptr;   // [R,3,3]
   size_t h0_cap = 0, rec_cap = 0;
+  float* clash_partial = nullptr;   // [CLASH_BATCH, parts, 4] partial clash forces (pose.cu), grow-only, sized by dfm_set_complex
+  size_t clash_cap = 0;
   uint64_t launches = 0;
   int num_sms = 148;
   // optional CUDA-event timing of the dominant (edge) kernel, for bench.py's roofline line
@@ -160,6 +162,8 @@ struct dfm_ctx {
 
 // Workspace carve-up for B trajectories (all offsets 256-byte aligned).
 constexpr int RING_FLAG_WORDS = 2048;
+constexpr int CLASH_BATCH = 1024;    // trajectories per clash-force launch pair (pose.cu)
+size_t clash_scratch_floats(int R, int L);
 struct Workspace {
   float* centre;     // [B,4]
   float* pos;        // [B,N,3,3] centred N/CA/C

@@ -195,64 +195,88 @@ k_reverse_step(int L, int all_atoms, int ode, float* __restrict__ lig_pos, float
 // Analytic gradient of the reference's autograd formulation.
 // Residue-pair pruning: the atoms of a residue lie within rho = max(|N-CA|, |C-CA|) of its CA, so a residue pair whose
 // CA-CA distance exceeds 4 + rho_l + rho_r has no atom pair inside the 4 A cut-off -- exact, not an approximation.
+// Work split: one CTA per (trajectory, tile of 64 receptor residues, slice of 32 ligand residues); a warp takes four ligand
+// residues of the slice, its lanes the receptor residues of the tile.  The partial forces of a trajectory's CTAs are summed in
+// a fixed order by k_clash_apply (bit-reproducible), which also moves the ligand.  (One CTA per trajectory, the first form of
+// this kernel, left 108 of 148 SMs idle at 40 trajectories and took 74 us of a 920 us step at BASELINE config #2.)
+constexpr int CLASH_RT = 64, CLASH_LS = 32;
 __global__ void __launch_bounds__(256)
-k_clash_force(int R, int L, const float* __restrict__ rec_pos, float* __restrict__ lig_pos,
-              float* __restrict__ tr_update) {
-  constexpr int TILE = 64;
+k_clash_partial(int R, int L, int nrt, const float* __restrict__ rec_pos, const float* __restrict__ lig_pos,
+                float* __restrict__ partial) {
   __shared__ float red[3][8];
-  __shared__ float rs[TILE * 10];       // per receptor residue: N, CA, C coordinates + rho
-  const int b = blockIdx.x, tid = threadIdx.x;
-  float* x = lig_pos + (size_t)b * L * 9;
+  __shared__ float rs[CLASH_RT * 10];       // per receptor residue: N, CA, C coordinates + rho
+  const int b = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rt = part % nrt, ls = part / nrt;
+  const int r0 = rt * CLASH_RT, cnt = min(CLASH_RT, R - r0);
+  const float* x = lig_pos + (size_t)b * L * 9;
+  for (int i = tid; i < cnt * 9; i += 256) rs[(i / 9) * 10 + (i % 9)] = rec_pos[(size_t)r0 * 9 + i];
+  __syncthreads();
+  if (tid < cnt) {
+    const float* q = rs + tid * 10;
+    const float ax = q[0] - q[3], ay = q[1] - q[4], az = q[2] - q[5];
+    const float cx = q[6] - q[3], cy = q[7] - q[4], cz = q[8] - q[5];
+    rs[tid * 10 + 9] = sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz));
+  }
+  __syncthreads();
   float fx = 0.f, fy = 0.f, fz = 0.f;
-  for (int r0 = 0; r0 < R; r0 += TILE) {
-    const int cnt = min(TILE, R - r0);
-    __syncthreads();
-    for (int i = tid; i < cnt * 9; i += 256) rs[(i / 9) * 10 + (i % 9)] = rec_pos[(size_t)r0 * 9 + i];
-    __syncthreads();
-    if (tid < cnt) {
-      const float* q = rs + tid * 10;
-      const float ax = q[0] - q[3], ay = q[1] - q[4], az = q[2] - q[5];
-      const float cx = q[6] - q[3], cy = q[7] - q[4], cz = q[8] - q[5];
-      rs[tid * 10 + 9] = sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz));
-    }
-    __syncthreads();
-    for (int l = tid; l < L; l += 256) {
-      float p[9];
+  for (int li = warp; li < CLASH_LS; li += 8) {
+    const int l = ls * CLASH_LS + li;
+    if (l >= L) break;
+    float p[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) p[k] = x[l * 9 + k];
-      const float ax = p[0] - p[3], ay = p[1] - p[4], az = p[2] - p[5];
-      const float cx = p[6] - p[3], cy = p[7] - p[4], cz = p[8] - p[5];
-      const float reach = 4.f + sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz)) + 1e-3f;
-      for (int r = 0; r < cnt; ++r) {
-        const float* q = rs + r * 10;
-        const float ex = p[3] - q[3], ey = p[4] - q[4], ez = p[5] - q[5];
-        const float lim = reach + q[9];
-        if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
+    for (int k = 0; k < 9; ++k) p[k] = x[l * 9 + k];
+    const float ax = p[0] - p[3], ay = p[1] - p[4], az = p[2] - p[5];
+    const float cx = p[6] - p[3], cy = p[7] - p[4], cz = p[8] - p[5];
+    const float reach = 4.f + sqrtf(fmaxf(ax * ax + ay * ay + az * az, cx * cx + cy * cy + cz * cz)) + 1e-3f;
+    for (int r = lane; r < cnt; r += 32) {
+      const float* q = rs + r * 10;
+      const float ex = p[3] - q[3], ey = p[4] - q[4], ez = p[5] - q[5];
+      const float lim = reach + q[9];
+      if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
 #pragma unroll
-        for (int la = 0; la < 3; ++la) {
+      for (int la = 0; la < 3; ++la) {
 #pragma unroll
-          for (int ra = 0; ra < 3; ++ra) {
-            const float dx = p[la * 3] - q[ra * 3], dy = p[la * 3 + 1] - q[ra * 3 + 1], dz = p[la * 3 + 2] - q[ra * 3 + 2];
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 < 16.f) {
-              const float d = sqrtf(d2);
-              const float g = 4.f - d;
-              const float sg = sqrtf(g);
-              const float dphi = -(1.5f * sg * d + g * sg) / (0.75f * d * d);
-              const float coef = -5.f * dphi / d;
-              fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
-            }
+        for (int ra = 0; ra < 3; ++ra) {
+          const float dx = p[la * 3] - q[ra * 3], dy = p[la * 3 + 1] - q[ra * 3 + 1], dz = p[la * 3 + 2] - q[ra * 3 + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < 16.f) {
+            const float d = sqrtf(d2);
+            const float g = 4.f - d;
+            const float sg = sqrtf(g);
+            const float dphi = -(1.5f * sg * d + g * sg) / (0.75f * d * d);
+            const float coef = -5.f * dphi / d;
+            fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
           }
         }
       }
     }
   }
   block_sum3(fx, fy, fz, red);
+  if (tid == 0) {
+    float* o = partial + ((size_t)b * gridDim.x + part) * 4;
+    o[0] = fx; o[1] = fy; o[2] = fz; o[3] = 0.f;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_clash_apply(int L, int nparts, const float* __restrict__ partial, float* __restrict__ lig_pos, float* __restrict__ tr_update) {
+  __shared__ float red[3][8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  for (int q = tid; q < nparts; q += 256) {      // fixed assignment and order: the same bits every run
+    const float* o = partial + ((size_t)b * nparts + q) * 4;
+    fx += o[0]; fy += o[1]; fz += o[2];
+  }
+  block_sum3(fx, fy, fz, red);
   const float inv = 1.f / (float)(L * 3);
   fx *= inv; fy *= inv; fz *= inv;
-  __syncthreads();
+  float* x = lig_pos + (size_t)b * L * 9;
   for (int l = tid; l < L * 3; l += 256) { x[l * 3] += fx; x[l * 3 + 1] += fy; x[l * 3 + 2] += fz; }
   if (tid == 0) { tr_update[b * 3] += fx; tr_update[b * 3 + 1] += fy; tr_update[b * 3 + 2] += fz; }
+}
+
+// floats of clash-force scratch a complex of R + L residues needs (dfm_set_complex allocates it, grow-only)
+size_t clash_scratch_floats(int R, int L) {
+  return (size_t)CLASH_BATCH * ((R + CLASH_RT - 1) / CLASH_RT) * ((L + CLASH_LS - 1) / CLASH_LS) * 4;
 }
 
 int launch_randomize_pose(dfm_ctx* ctx, int B, const float* lig0, const float* rot0, const float* tr0, uint64_t seed,
@@ -273,8 +297,17 @@ int launch_reverse_step(dfm_ctx* ctx, int B, float* lig_pos, float* rot_update, 
                                    stream_base, step);
   LAUNCH_CHECK(ctx);
   if (flags & DFM_CLASH_FORCE) {
-    k_clash_force<<<B, 256, 0, s>>>(ctx->R, ctx->L, ctx->rec_pos, lig_pos, tr_update);
-    LAUNCH_CHECK(ctx);
+    const int nrt = (ctx->R + CLASH_RT - 1) / CLASH_RT, nls = (ctx->L + CLASH_LS - 1) / CLASH_LS;
+    const int nparts = nrt * nls;
+    // scratch of CLASH_BATCH trajectories' partial forces, allocated by dfm_set_complex (nothing is allocated here)
+    for (int b0 = 0; b0 < B; b0 += CLASH_BATCH) {
+      const int nb = min(CLASH_BATCH, B - b0);
+      k_clash_partial<<<dim3(nparts, nb), 256, 0, s>>>(ctx->R, ctx->L, nrt, ctx->rec_pos, lig_pos + (size_t)b0 * ctx->L * 9,
+                                                     ctx->clash_partial);
+      LAUNCH_CHECK(ctx);
+      k_clash_apply<<<nb, 256, 0, s>>>(ctx->L, nparts, ctx->clash_partial, lig_pos + (size_t)b0 * ctx->L * 9, tr_update + (size_t)b0 * 3);
+      LAUNCH_CHECK(ctx);
+    }
   }
   return 0;
 }

@@ -17,8 +17,9 @@
  *   - all work is stream-ordered on the cudaStream_t passed as `stream` (a void* here so that the
  *     header needs no CUDA include).  Entry points that synchronise: dfm_create, dfm_finalize_weights,
  *     dfm_destroy (device / stream), dfm_profile_read (its own events), and dfm_set_complex ONLY when the
- *     complex is larger than the context's grow-only arena (4096 residues up front, doubled on demand):
- *     then it synchronises `stream` once and re-allocates.  Nothing else synchronises or allocates.
+ *     complex is larger than the context's grow-only arena (4096 residues up front, doubled on demand; the
+ *     arena also holds the clash-force scratch of dfm_reverse_step / dfm_sample): then it synchronises
+ *     `stream` once and re-allocates.  Nothing else synchronises or allocates.
  *   - one context per (device, stream); contexts are independent; a context is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device every entry point fails with DFM_ECUDA.
  */
