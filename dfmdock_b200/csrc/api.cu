@@ -218,10 +218,22 @@ extern "C" int dfm_finalize_weights(dfm_ctx* ctx, float cut_off, void* stream) {
   if ((rc = launch_image_pack(ctx, ctx->We, 512, 0, 1.f, ctx->img_WeR, s))) return rc;
   if ((rc = launch_image_pack(ctx, ctx->We, 512, 256, 1.f, ctx->img_WeL, s))) return rc;
   NEED("t_embed.0.W", {DFM_INNER_DIM / 2}); ctx->t_W = tmp;
-  NEED("t_embed.1.weight", {DFM_INNER_DIM, DFM_INNER_DIM}); ctx->t_lin = tmp;
+  // the head's small Linear layers are applied one output per thread: stored transposed ([in, out]) the 128 threads of a CTA
+  // read consecutive addresses
+  {
+    float* tl;
+    NEED("t_embed.1.weight", {DFM_INNER_DIM, DFM_INNER_DIM});
+    if ((rc = dev_alloc(ctx, &tl, (size_t)DFM_INNER_DIM * DFM_INNER_DIM))) return rc;
+    if ((rc = launch_transpose(ctx, tmp, DFM_INNER_DIM, DFM_INNER_DIM, tl, s))) return rc;
+    ctx->t_lin = tl;
+  }
   const char* sc[2] = {"tr_scale", "rot_scale"};
   for (int q = 0; q < 2; ++q) {
-    NEED(std::string(sc[q]) + ".0.weight", {DFM_INNER_DIM, DFM_INNER_DIM + 1}); ctx->sc_W1[q] = tmp;
+    float* w1t;
+    NEED(std::string(sc[q]) + ".0.weight", {DFM_INNER_DIM, DFM_INNER_DIM + 1});
+    if ((rc = dev_alloc(ctx, &w1t, (size_t)DFM_INNER_DIM * (DFM_INNER_DIM + 1)))) return rc;
+    if ((rc = launch_transpose(ctx, tmp, DFM_INNER_DIM, DFM_INNER_DIM + 1, w1t, s))) return rc;
+    ctx->sc_W1[q] = w1t;
     NEED(std::string(sc[q]) + ".1.weight", {DFM_INNER_DIM}); ctx->sc_lnw[q] = tmp;
     NEED(std::string(sc[q]) + ".1.bias", {DFM_INNER_DIM}); ctx->sc_lnb[q] = tmp;
     NEED(std::string(sc[q]) + ".4.weight", {1, DFM_INNER_DIM}); ctx->sc_w2[q] = tmp;

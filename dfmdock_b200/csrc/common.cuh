@@ -131,8 +131,8 @@ struct dfm_ctx {
   __half* img_WeR = nullptr;
   __half* img_WeL = nullptr;
   const float* t_W = nullptr;     // t_embed.0.W [64]
-  const float* t_lin = nullptr;   // t_embed.1.weight [128,128]
-  const float* sc_W1[2] = {nullptr, nullptr};  // tr_scale / rot_scale .0.weight [128,129]
+  const float* t_lin = nullptr;   // t_embed.1.weight transposed: [in 128, out 128]
+  const float* sc_W1[2] = {nullptr, nullptr};  // tr_scale / rot_scale .0.weight transposed: [in 129, out 128]
   const float* sc_lnw[2] = {nullptr, nullptr};
   const float* sc_lnb[2] = {nullptr, nullptr};
   const float* sc_w2[2] = {nullptr, nullptr};  // .4.weight [128]

@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(128) k_force_head(int N, int R, const float* _
   __syncthreads();
   {
     float acc = 0.f;
-    const float* wr = hw.t_lin + (size_t)tid * 128;
-    for (int k = 0; k < 128; ++k) acc = fmaf(wr[k], four[k], acc);
+    const float* wc = hw.t_lin + tid;                      // [in, out]: coalesced over the CTA
+#pragma unroll 32
+    for (int k = 0; k < 128; ++k) acc = fmaf(__ldg(wc + k * 128), four[k], acc);
     temb[tid] = sigmoid_acc(acc);
   }
   __syncthreads();
@@ -266,9 +267,10 @@ __global__ void __launch_bounds__(128) k_force_head(int N, int R, const float* _
   for (int which = 0; which < 2; ++which) {
     const float vx = pred[which * 3], vy = pred[which * 3 + 1], vz = pred[which * 3 + 2];
     const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
-    const float* wr = hw.W1[which] + (size_t)tid * 129;
-    float yv = wr[0] * nrm;
-    for (int k = 0; k < 128; ++k) yv = fmaf(wr[1 + k], temb[k], yv);
+    const float* wc = hw.W1[which] + tid;                  // [in 129, out 128]
+    float yv = __ldg(wc) * nrm;
+#pragma unroll 32
+    for (int k = 0; k < 128; ++k) yv = fmaf(__ldg(wc + (1 + k) * 128), temb[k], yv);
     const float mean = block_sum128(yv, red) / 128.f;
     const float dv = yv - mean;
     const float var = block_sum128(dv * dv, red) / 128.f;
