@@ -234,18 +234,19 @@ __device__ __forceinline__ void coord_body(const Params& p, const CUtensorMap& t
 
     // residue of tile row `r64` (0 / 1): stand-alone: ligand residue tile * 2 + r64 of B * L; fused: residue ptile * 2 + r64
     // of the node-pair grid, a ligand residue or not.  -> global row gi (or -1) and index into fbuf
-    auto residue = [&](int tile, int r64, int& lig_index) -> long {
+    // (32-bit arithmetic only: this runs once per tile in the four cq == 0 warps while the other twelve wait at the barrier)
+    auto residue = [&](int tile, int r64, int& lig_index, int& b) -> int {
       if (!FUSED) {
         const int node = tile * 2 + r64;
         lig_index = node;
-        if (node >= total) return -1;
-        const int b = node / L, i = p.R + node % L;
-        return (long)b * p.N + i;
+        b = node / L;
+        return node < total ? b * p.N + p.R + (node - b * L) : -1;
       }
       const int node = ring_phys(ring, tile) * 2 + r64;
-      const int b = node / p.N, i = node - b * p.N;
+      b = node / p.N;
+      const int i = node - b * p.N;
       lig_index = b * L + i - p.R;
-      return (node < ring.total_nodes && i >= p.R) ? (long)node : -1;
+      return (node < ring.total_nodes && i >= p.R) ? node : -1;
     };
     int it = 0;
     for (int item = cta; item < n_items; item += ncta) {
@@ -258,11 +259,10 @@ __device__ __forceinline__ void coord_body(const Params& p, const CUtensorMap& t
       float gx = 0.f, gy = 0.f, gz = 0.f;
       if (cq == 0) {
         const int k = erow & 63;
-        int li;
-        const long gl = residue(tile, erow >> 6, li);
+        int li, b;
+        const int gl = residue(tile, erow >> 6, li, b);
         if (gl >= 0 && k < p.K) {
           const size_t gi = (size_t)gl;
-          const int b = (int)(gl / p.N);
           const int j = __ldg(p.nbr + gi * SLOTS + k);
           const float* pi = p.pos + gi * 9 + 3;
           const float* pj = p.pos + ((size_t)b * p.N + j) * 9 + 3;
@@ -299,7 +299,7 @@ __device__ __forceinline__ void coord_body(const Params& p, const CUtensorMap& t
       // the four column quarters of a row meet in shared memory (double buffered by tile parity: only the cq == 0 warps
       // go on to the reduction, the other twelve move straight to the next tile)
       part[buf * 512 + cq * 128 + erow] = dotp;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");     // only the four warps that share this row quarter meet
       if (cq == 0) {
         const float* pp = part + buf * 512;
         const float tot = (pp[erow] + pp[128 + erow]) + (pp[256 + erow] + pp[384 + erow]);
@@ -307,10 +307,10 @@ __device__ __forceinline__ void coord_body(const Params& p, const CUtensorMap& t
         const float fx = warp_sum(gx * w), fy = warp_sum(gy * w), fz = warp_sum(gz * w);
         float* fp = fpart + buf * 16;
         if (lane == 0) { fp[q * 4] = fx; fp[q * 4 + 1] = fy; fp[q * 4 + 2] = fz; }
-        asm volatile("bar.sync 2, 128;" ::: "memory");          // the four row-quarter warps
+        asm volatile("bar.sync 5, 128;" ::: "memory");          // the four row-quarter warps
         if (tid < 2) {
-          int nd;
-          if (residue(tile, tid, nd) >= 0) {
+          int nd, bb;
+          if (residue(tile, tid, nd, bb) >= 0) {
             float* fo = p.fbuf + (size_t)nd * 4;
             fo[0] = fp[(2 * tid) * 4] + fp[(2 * tid + 1) * 4];
             fo[1] = fp[(2 * tid) * 4 + 1] + fp[(2 * tid + 1) * 4 + 1];
