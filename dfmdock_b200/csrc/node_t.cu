@@ -110,6 +110,9 @@ enum Mode { MODE_AB = 0, MODE_Z = 1, MODE_H = 2 };
 #ifndef NTT_AB_ROWS
 #define NTT_AB_ROWS 128   // rows per MODE_AB tile (64 or 128)
 #endif
+#ifndef NTT_AB_ISSUERS
+#define NTT_AB_ISSUERS 2
+#endif
 #ifndef NTT_BULK_W
 #define NTT_BULK_W 1   // weight image by cp.async.bulk (TMA 1-D) overlapped with the set-up instead of 14 rounds of LDG + STS
 #endif
@@ -160,6 +163,10 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p, const __grid_co
   constexpr bool SPLIT = (MODE == MODE_AB || MODE == MODE_Z);
   constexpr int TCOLS = NHALF * ROWS;                      // TMEM columns of one accumulator buffer: 128 or 256
   constexpr int NACCM = 512 / TCOLS < NACC ? 512 / TCOLS : NACC;
+  // MMA issuers: the issue path costs ~130-160 cycles per tcgen05.mma and MODE_AB's issuer was busy 88 % of the launch
+  // (NTT_TIMING), so its two feature halves are issued by two threads (warps NWORK + 2 and NWORK + 1), each into its own
+  // accumulator columns; an operand slot is free / a tile is ready when both have committed
+  constexpr int NISSUE = (MODE == MODE_AB && NTT_AB_ISSUERS == 2) ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -192,9 +199,9 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p, const __grid_co
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + 8 * i, MODE == MODE_H ? NWORK * 32 : 1); mbar_init(bar_empty + 8 * i, NISSUE); }
     if (MODE != MODE_H) { tma_prefetch_desc(&tmX); if (MODE == MODE_Z) tma_prefetch_desc(&tmX2); }
-    for (int i = 0; i < NACCM; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NWORK * 32); }
+    for (int i = 0; i < NACCM; ++i) { mbar_init(bar_accf + 8 * i, NISSUE); mbar_init(bar_acce + 8 * i, NWORK * 32); }
 #if NTT_BULK_W
     mbar_init(bar_w, 1);
 #endif
@@ -224,8 +231,10 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p, const __grid_co
   if (NTT_TIMING && tid == 0) atomicAdd(p.timing + 0, (unsigned long long)(t_start - t_kernel));
   unsigned long long tw0 = 0, tw1 = 0;
 
-  if (warp == NWORK + 2) {
-    // =================================== MMA ISSUER ===================================================
+  if (warp == NWORK + 2 || (NISSUE == 2 && warp == NWORK + 1)) {
+    // =================================== MMA ISSUER(S) ================================================
+    const int hf0 = (NISSUE == 2) ? (warp == NWORK + 2 ? 0 : 1) : 0;          // first feature half of this issuer
+    const int hf1 = (NISSUE == 2) ? hf0 + 1 : NHALF;
     if (lane == 0) {
       const uint64_t dW = make_desc(sbase + OFF_W);
       const uint64_t dS = make_desc(sbase + OFF_S);
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(NT, 1) k_nodeT(const Params p, const __grid_co
           tc_fence_after();
 #pragma unroll
           for (int hf = 0; hf < NHALF; ++hf) {
+            if (hf < hf0 || hf >= hf1) continue;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               // A = weight rows [hf*128, +128) of K block kb; B = activation rows of ring slot `slot`
