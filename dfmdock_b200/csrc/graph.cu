@@ -272,152 +272,200 @@ k_graph(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ p
 // order-preserving unsigned bit patterns of non-negative floats.  The k-th smallest key is found most-significant
 // bit first (one compare per element and one REDUX per bit, starting below the common prefix of all keys), ties at
 // the threshold go to the smaller residue index (like k_graph); members are compacted to slots with warp ballots.
-template <int WARPS, int S>
+template <int WARPS, int S, bool STAGE>
 __global__ void __launch_bounds__(WARPS * 32)
-k_graph_sel(int B, int N, int R, int K, int knn, int ns, const float* __restrict__ pos, const float* __restrict__ cb,
-            const float* __restrict__ exp_noise, uint64_t seed, uint64_t stream_base, uint32_t fwd,
-            int32_t* __restrict__ nbr, uint32_t* __restrict__ feat, float* __restrict__ radial, int4* __restrict__ emeta) {
+k_graph_sel(int B, int N, int R, int K, int knn, int ns, int rpc, int cpt, const float* __restrict__ pos,
+            const float* __restrict__ cb, const float* __restrict__ exp_noise, uint64_t seed, uint64_t stream_base,
+            uint32_t fwd, int32_t* __restrict__ nbr, uint32_t* __restrict__ feat, float* __restrict__ radial,
+            int4* __restrict__ emeta) {
   __shared__ float s_e[WARPS][S * 32];        // Exp(1) draws in residue order (Philox blocks cover 4 residues each)
   __shared__ int s_slot[WARPS][SLOTS];
+  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(16) unsigned char s_tile[];   // the trajectory's backbone [N,3,3] and virtual CB [N,4], staged by TMA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * WARPS + warp;
-  if (row >= (long)B * N) return;
-  const int b = (int)(row / N), i = (int)(row % N);
+  // CTA = rows [c * rpc, (c + 1) * rpc) of ONE trajectory b (cpt CTAs per trajectory).
+  // STAGE: the trajectory's coordinates are brought into shared memory once per CTA by two bulk copies (cp.async.bulk,
+  // completion by transaction bytes on an mbarrier) and every distance / pair feature of the CTA's rows is computed from
+  // there; rpc is chosen by the launcher so that the copy is amortised over several rows per warp while the grid still
+  // fills the GPU several times over.  The [N,9] float block starts on a 4-byte boundary only: the copy starts at the
+  // 16-byte boundary below it.  Measured on B200 at 2x150 residues x 256 trajectories: 421 us staged vs 386 us reading the
+  // same 15.6 KB per trajectory through L1 (same 325 M warp instructions; the staged form loses 4 % to its coarser grid
+  // and 4 % of issue rate to shared-memory bank conflicts of the random-neighbour reads), so the direct form is the
+  // default and DFM_GRAPH_STAGE=1 selects this one (tests/test_gpu_parity.py checks that both give the same graph).
+  const int b = (int)blockIdx.x / cpt, c = (int)blockIdx.x - b * cpt;
   const size_t gbase = (size_t)b * N;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-
-  // ---- distances (float bits; absent -> 0xFFFFFFFF)
-  uint32_t kd[S];
-  {
-    const float* pi = pos + (gbase + i) * 9;
-    const float xi = pi[3], yi = pi[4], zi = pi[5];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int j = lane + 32 * s;
-      kd[s] = 0xFFFFFFFFu;
-      if (j < N) {
-        const float* pj = pos + (gbase + j) * 9;
-        const float dx = xi - pj[3], dy = yi - pj[4], dz = zi - pj[5];
-        kd[s] = __float_as_uint(sqrtf(dx * dx + dy * dy + dz * dz));
-      }
+  const float* P = pos + gbase * 9;             // trajectory-local views (residue j at P + 9 j, CB + 4 j)
+  const float* CB = cb + gbase * 4;
+  if (STAGE) {
+    const uintptr_t psrc = reinterpret_cast<uintptr_t>(pos + gbase * 9);
+    const uint32_t lead = (uint32_t)(psrc & 15u);
+    const uint32_t pbytes = (lead + (uint32_t)N * 36u + 15u) & ~15u, cbytes = (uint32_t)N * 16u;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tile);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pbytes + cbytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(psrc - lead), "r"(pbytes), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + pbytes), "l"(cb + gbase * 4), "r"(cbytes), "r"(bar) : "memory");
     }
+    __syncthreads();                             // the barrier is initialised before anyone waits on it
+    uint32_t ok = 0, tries = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar) : "memory");
+      if (!ok && ++tries > (1u << 24)) __trap();
+    }
+    P = reinterpret_cast<const float*>(s_tile + lead);
+    CB = reinterpret_cast<const float*>(s_tile + pbytes);
   }
-  // k-th smallest of the present keys, then membership flags with ties to the smaller index
-  auto select = [&](const uint32_t (&key)[S], int k, uint32_t& member) {
-    // common prefix: skip the bits on which min and max agree
-    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      if (key[s] != 0xFFFFFFFFu) { mn = min(mn, key[s]); mx = max(mx, key[s]); }
-    }
-    mn = __reduce_min_sync(0xffffffffu, mn);
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    uint32_t v = mn;
-    bool exact = false;            // true: {key < v} has exactly k members
-    if (mn != mx) {
-      const int top = 31 - __clz(mn ^ mx);            // highest differing bit
-      v = (top == 31) ? 0u : (mn >> (top + 1)) << (top + 1);
-      for (int bit = top; bit >= 0; --bit) {
-        const uint32_t test = v | (1u << bit);
-        int cnt = 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) cnt += (key[s] < test) ? 1 : 0;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt == k) { v = test; exact = true; break; }
-        if (cnt < k) v = test;
-      }
-    }
-    member = 0u;                    // bit s: element s of this lane is selected
-    if (exact) {
-#pragma unroll
-      for (int s = 0; s < S; ++s) member |= (key[s] < v) ? (1u << s) : 0u;
-    } else {
-      int less = 0;
-#pragma unroll
-      for (int s = 0; s < S; ++s) less += (key[s] < v) ? 1 : 0;
-      less = __reduce_add_sync(0xffffffffu, less);
-      int need = k - less;          // how many of the keys equal to v to take, smallest index first
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  auto do_row = [&](const int i) {
+    // ---- distances (float bits; absent -> 0xFFFFFFFF)
+    uint32_t kd[S];
+    {
+      const float* pi = P + (size_t)i * 9;
+      const float xi = pi[3], yi = pi[4], zi = pi[5];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const bool eq = key[s] == v && key[s] != 0xFFFFFFFFu;
-        const uint32_t bal = __ballot_sync(0xffffffffu, eq);
-        const bool take = eq && (int)__popc(bal & lt_mask) < need;
-        member |= ((key[s] < v) || take) ? (1u << s) : 0u;
-        need -= min(need, (int)__popc(bal));
+        const int j = lane + 32 * s;
+        kd[s] = 0xFFFFFFFFu;
+        if (j < N) {
+          const float* pj = P + (size_t)j * 9;
+          const float dx = xi - pj[3], dy = yi - pj[4], dz = zi - pj[5];
+          kd[s] = __float_as_uint(sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+      }
+    }
+    // k-th smallest of the present keys, then membership flags with ties to the smaller index
+    auto select = [&](const uint32_t (&key)[S], int k, uint32_t& member) {
+      // common prefix: skip the bits on which min and max agree
+      uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (key[s] != 0xFFFFFFFFu) { mn = min(mn, key[s]); mx = max(mx, key[s]); }
+      }
+      mn = __reduce_min_sync(0xffffffffu, mn);
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      uint32_t v = mn;
+      bool exact = false;            // true: {key < v} has exactly k members
+      if (mn != mx) {
+        const int top = 31 - __clz(mn ^ mx);            // highest differing bit
+        v = (top == 31) ? 0u : (mn >> (top + 1)) << (top + 1);
+        for (int bit = top; bit >= 0; --bit) {
+          const uint32_t test = v | (1u << bit);
+          int cnt = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) cnt += (key[s] < test) ? 1 : 0;
+          cnt = __reduce_add_sync(0xffffffffu, cnt);
+          if (cnt == k) { v = test; exact = true; break; }
+          if (cnt < k) v = test;
+        }
+      }
+      member = 0u;                    // bit s: element s of this lane is selected
+      if (exact) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) member |= (key[s] < v) ? (1u << s) : 0u;
+      } else {
+        int less = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) less += (key[s] < v) ? 1 : 0;
+        less = __reduce_add_sync(0xffffffffu, less);
+        int need = k - less;          // how many of the keys equal to v to take, smallest index first
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const bool eq = key[s] == v && key[s] != 0xFFFFFFFFu;
+          const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+          const bool take = eq && (int)__popc(bal & lt_mask) < need;
+          member |= ((key[s] < v) || take) ? (1u << s) : 0u;
+          need -= min(need, (int)__popc(bal));
+        }
+      }
+    };
+
+    uint32_t mem1;
+    select(kd, knn, mem1);
+    // slots of the kNN members (index order) and, for injected noise, the rank of every residue among the non-members
+    int base = 0;
+    int nonmember_before[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool m = (mem1 >> s) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, m);
+      const int below = base + (int)__popc(bal & lt_mask);      // members with a smaller index
+      if (m) s_slot[warp][below] = lane + 32 * s;
+      nonmember_before[s] = (lane + 32 * s) - below;            // compacted column of this residue in the noise row
+      base += (int)__popc(bal);
+    }
+    // ---- exponential race over the remaining residues: key = Exp(1) * d^3, keep the ns smallest
+    if (ns > 0) {
+      if (exp_noise == nullptr) {
+        const uint64_t strm = stream_base + (uint64_t)b;
+        for (int q = lane; q * 4 < N; q += 32) {               // Philox block q covers residues 4q .. 4q+3
+          const uint4 r4 = dfm_rng(seed, strm, RNG_EDGE, fwd, (uint32_t)q, (uint32_t)i);
+          *reinterpret_cast<float4*>(&s_e[warp][q * 4]) =
+              make_float4(-logf(u01_open(r4.x)), -logf(u01_open(r4.y)), -logf(u01_open(r4.z)), -logf(u01_open(r4.w)));
+        }
+        __syncwarp();
+      }
+      uint32_t k2[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int j = lane + 32 * s;
+        k2[s] = 0xFFFFFFFFu;
+        if (j < N && !((mem1 >> s) & 1u)) {
+          const float e = exp_noise ? exp_noise[(gbase + i) * (size_t)(N - knn) + nonmember_before[s]] : s_e[warp][j];
+          const float d = fmaxf(__uint_as_float(kd[s]), 1e-10f);
+          k2[s] = min(__float_as_uint(e * (d * d * d)), 0xFFFFFFFEu);
+        }
+      }
+      uint32_t mem2;
+      select(k2, ns, mem2);
+      int base2 = knn;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const bool m = (mem2 >> s) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (m) s_slot[warp][base2 + (int)__popc(bal & lt_mask)] = lane + 32 * s;
+        base2 += (int)__popc(bal);
+      }
+    }
+    __syncwarp();
+    // ---- pair features for the K selected edges; pad slots point at the residue itself
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k = lane + 32 * half;
+      int j = i;
+      uint32_t ft = 0;
+      float r2 = 0.f;
+      if (k < K) {
+        j = min(max(s_slot[warp][k], 0), N - 1);
+        ft = pair_bins(P, CB, i, j, i, j, R, &r2);
+      }
+      const size_t o = (gbase + i) * SLOTS + k;
+      nbr[o] = j;
+      feat[o] = ft;
+      radial[o] = r2;
+      {
+        const uint32_t otp = (ft >> 6) & 0x3FFFu;
+        const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
+        const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
+        const __half2 rh = __float2half2_rn(fminf(r2 * 0.03125f, 65000.f));
+        emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, *reinterpret_cast<const int*>(&rh));
       }
     }
   };
-
-  uint32_t mem1;
-  select(kd, knn, mem1);
-  // slots of the kNN members (index order) and, for injected noise, the rank of every residue among the non-members
-  int base = 0;
-  int nonmember_before[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const bool m = (mem1 >> s) & 1u;
-    const uint32_t bal = __ballot_sync(0xffffffffu, m);
-    const int below = base + (int)__popc(bal & lt_mask);      // members with a smaller index
-    if (m) s_slot[warp][below] = lane + 32 * s;
-    nonmember_before[s] = (lane + 32 * s) - below;            // compacted column of this residue in the noise row
-    base += (int)__popc(bal);
-  }
-  // ---- exponential race over the remaining residues: key = Exp(1) * d^3, keep the ns smallest
-  if (ns > 0) {
-    if (exp_noise == nullptr) {
-      const uint64_t strm = stream_base + (uint64_t)b;
-      for (int q = lane; q * 4 < N; q += 32) {               // Philox block q covers residues 4q .. 4q+3
-        const uint4 r4 = dfm_rng(seed, strm, RNG_EDGE, fwd, (uint32_t)q, (uint32_t)i);
-        *reinterpret_cast<float4*>(&s_e[warp][q * 4]) =
-            make_float4(-logf(u01_open(r4.x)), -logf(u01_open(r4.y)), -logf(u01_open(r4.z)), -logf(u01_open(r4.w)));
-      }
-      __syncwarp();
+  if (STAGE) {
+    const int i_end = min(N, (c + 1) * rpc);
+    for (int i = c * rpc + warp; i < i_end; i += WARPS) {
+      do_row(i);
+      __syncwarp();      // s_e / s_slot of this warp are reused by its next row
     }
-    uint32_t k2[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int j = lane + 32 * s;
-      k2[s] = 0xFFFFFFFFu;
-      if (j < N && !((mem1 >> s) & 1u)) {
-        const float e = exp_noise ? exp_noise[(gbase + i) * (size_t)(N - knn) + nonmember_before[s]] : s_e[warp][j];
-        const float d = fmaxf(__uint_as_float(kd[s]), 1e-10f);
-        k2[s] = min(__float_as_uint(e * (d * d * d)), 0xFFFFFFFEu);
-      }
-    }
-    uint32_t mem2;
-    select(k2, ns, mem2);
-    int base2 = knn;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const bool m = (mem2 >> s) & 1u;
-      const uint32_t bal = __ballot_sync(0xffffffffu, m);
-      if (m) s_slot[warp][base2 + (int)__popc(bal & lt_mask)] = lane + 32 * s;
-      base2 += (int)__popc(bal);
-    }
-  }
-  __syncwarp();
-  // ---- pair features for the K selected edges; pad slots point at the residue itself
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int k = lane + 32 * half;
-    int j = i;
-    uint32_t ft = 0;
-    float r2 = 0.f;
-    if (k < K) {
-      j = min(max(s_slot[warp][k], 0), N - 1);
-      ft = pair_bins(pos, cb, (int)(gbase + i), (int)(gbase + j), i, j, R, &r2);
-    }
-    const size_t o = (gbase + i) * SLOTS + k;
-    nbr[o] = j;
-    feat[o] = ft;
-    radial[o] = r2;
-    {
-      const uint32_t otp = (ft >> 6) & 0x3FFFu;
-      const int drp = (int)(((otp == 0 ? 40u : 0u) + (ft & 63u)) * 66u + ((k < K) ? ((ft >> 20) & 127u) : 32u));
-      const int oidx = (int)((((ft >> 6) & 31u) * 24u + ((ft >> 11) & 31u)) * 12u + ((ft >> 16) & 15u));
-      const __half2 rh = __float2half2_rn(fminf(r2 * 0.03125f, 65000.f));
-      emeta[o] = make_int4((int)(gbase + j), drp, otp == 0 ? -1 : oidx, *reinterpret_cast<const int*>(&rh));
-    }
+  } else {               // one row per warp (rpc == WARPS)
+    const int i = c * WARPS + warp;
+    if (i < N) do_row(i);
   }
 }
 
@@ -617,9 +665,27 @@ template <int WARPS, int S>
 static int launch_graph_sel_w(dfm_ctx* ctx, int B, const float* exp_noise, uint64_t seed, uint64_t stream_base,
                               uint32_t fwd_index, Workspace& ws, cudaStream_t s) {
   const long rows = (long)B * ctx->N;
-  const int grid = (int)((rows + WARPS - 1) / WARPS);
-  k_graph_sel<WARPS, S><<<grid, WARPS * 32, 0, s>>>(B, ctx->N, ctx->R, ctx->K, ctx->knn, ctx->ns, ws.pos, ws.cb, exp_noise,
-                                                   seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
+  static int stage = -1;
+  if (stage < 0) { const char* e = getenv("DFM_GRAPH_STAGE"); stage = e ? atoi(e) : 0; }
+  if (!stage) {       // one row per warp, coordinates read through L1
+    const int cpt = (ctx->N + WARPS - 1) / WARPS;
+    k_graph_sel<WARPS, S, false><<<B * cpt, WARPS * 32, 0, s>>>(B, ctx->N, ctx->R, ctx->K, ctx->knn, ctx->ns, WARPS, cpt, ws.pos, ws.cb,
+                                                               exp_noise, seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
+    LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  const size_t dyn = (((size_t)ctx->N * 36 + 15 + 15) & ~(size_t)15) + (size_t)ctx->N * 16;   // staged coordinates of one trajectory
+  static unsigned long long attr_devices = 0;
+  if (dfm_once_per_device(attr_devices, ctx->device))
+    CUDA_TRY(cudaFuncSetAttribute(k_graph_sel<WARPS, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  // rows per CTA: enough CTAs for ~12 waves of 3 CTAs per SM, at least one row per warp, at most 8 rows per warp
+  long rpc = rows / ((long)ctx->num_sms * 36);
+  rpc = (rpc + WARPS - 1) / WARPS * WARPS;
+  if (rpc < WARPS) rpc = WARPS;
+  if (rpc > 8 * WARPS) rpc = 8 * WARPS;
+  const int cpt = (int)((ctx->N + rpc - 1) / rpc);
+  k_graph_sel<WARPS, S, true><<<B * cpt, WARPS * 32, dyn, s>>>(B, ctx->N, ctx->R, ctx->K, ctx->knn, ctx->ns, (int)rpc, cpt, ws.pos, ws.cb,
+                                                              exp_noise, seed, stream_base, fwd_index, ws.nbr, ws.feat, ws.radial, ws.emeta);
   LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -7,6 +7,8 @@ Tolerances (stated per mode):
   integer outputs (bins, num_clashes, neighbour sets with injected noise): exact, except pair-feature bins whose
   angle lies within 1e-3 degree of a bin edge (libm vs CUDA atan2/acos): at most 0.05% of the bins may differ.
 """
+import os
+
 import pytest
 import torch
 
@@ -218,6 +220,41 @@ def test_large_complex_graph_kernel_equals_generic_kernel(n_rec, n_lig):
         assert torch.equal(a[:, :, 20:].sort(-1).values, b[:, :, 20:].sort(-1).values), (n_rec, n_lig, exp is not None)
         if noise is None:
             break
+
+
+def test_tma_staged_graph_kernel_equals_direct_kernel(tmp_path):
+    """DFM_GRAPH_STAGE=1 (read once per process, hence the subprocess): the graph kernel stages a trajectory's coordinates in
+    shared memory with cp.async.bulk and loops over several rows per warp.  Same arithmetic -> identical neighbour tables,
+    packed bins and scores, for sizes that use 10 / 16 / 32 keys per lane, an odd N (unaligned copy source) and N < 60."""
+    import subprocess, sys
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from dfmdock_b200 import Score_Model
+from dfmdock_b200.features import synthetic_complex
+from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+sd, hp = synthetic_state_dict(0, 66), synthetic_hparams(66)
+out = {}
+for n_rec, n_lig, B in ((40, 30, 3), (25, 20, 5), (150, 151, 9), (260, 190, 4), (600, 301, 2)):
+    batch = synthetic_complex(n_rec, n_lig, seed=2)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([12.0, 0.0, 0.0])
+    model = Score_Model(sd, hp, precision="fp16").to("cuda")
+    model.set_complex(batch)
+    lig = batch["lig_pos"][None].repeat(B, 1, 1, 1)
+    o = model.score(lig, torch.full((B,), 0.4), seed=3, stream_base=7, forward_index=5, return_edges=True)
+    out[(n_rec, n_lig)] = (o["edges"].cpu(), o["f"].cpu())
+torch.save(out, sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("direct", {}), ("staged", {"DFM_GRAPH_STAGE": "1"})):
+        e = dict(os.environ); e.update(env)
+        f = str(tmp_path / (tag + ".pt"))
+        r = subprocess.run([sys.executable, "-c", code, f], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = torch.load(f)
+    for k in res["direct"]:
+        assert torch.equal(res["direct"][k][0], res["staged"][k][0]), k
+        assert torch.equal(res["direct"][k][1], res["staged"][k][1]), k
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
