@@ -23,8 +23,10 @@
 //
 // All operands are pre-halved at production (A, B, tables, w1r, W2, b2 carry a factor 1/2), because
 // SiLU(x) = h + h * tanh(h) with h = x/2: two MUFU (tanh.approx.f16x2 has no packed form) and one HFMA2 per element pair.
+// The last layer without the energy head can also run as ONE launch with the coordinate head (k_last_fused, last_ring.cuh).
 // Build switches (-D...): EWS_TIMING (per-role wait cycles), EWS_EXP (diagnostic, wrong results), EWS_*_REGS, EWS_SLEEP_*,
-// EWS_FOLD, EWS_BIAS_MMA, EWS_PIN_ADDR, EWS_BULK_W; profiles/r01/README.md lists what each measured.
+// EWS_FOLD, EWS_BIAS_MMA, EWS_PIN_ADDR, EWS_BULK_W (profiles/r01/README.md lists what each measured); EWS_RELAY, EWS_NLOAD,
+// EWS_LOAD_BYKB, EWS_WAIT_HINT (round 2, profiles/r02/README.md and DESIGN.md section 4).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -61,7 +63,7 @@ constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for the manual 102
 
 constexpr int NPROD = 16;                // producer warps
 constexpr int NEPI = 8;                  // epilogue warps
-// 28 warps: 16 producers, 8 epilogue, 1 MMA issuer + 2 loaders + 1 idle warp that completes the warpgroup (setmaxnreg is a
+// 28 warps: 16 producers, 8 epilogue, 1 MMA issuer + 2 loaders + 1 relay warp; the last four form one warpgroup (setmaxnreg is a
 // warpgroup-wide operation: a lone 17th warp never finishes it and the epilogue's .inc then blocks forever).
 constexpr int NT = (NPROD + NEPI + 4) * 32;   // 896 -> 72 registers/thread at launch, pool 28*32*72 = 64512
 #ifndef EWS_PROD_REGS
