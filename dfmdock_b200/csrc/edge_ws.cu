@@ -242,6 +242,9 @@ __device__ __forceinline__ float2 h2f2(uint32_t a) {
 }
 // SiLU(2h) = h + h * tanh(h)
 __device__ __forceinline__ uint32_t h2silu(uint32_t h) { return (EWS_EXP & 4) ? h2fma(h, h, h) : h2fma(h, h2tanh(h), h); }
+// diagnostic split of EWS_EXP 4: 32 = no tanh in the producers only, 64 = no tanh in the epilogue only
+__device__ __forceinline__ uint32_t h2silu_p(uint32_t h) { return (EWS_EXP & 32) ? h2fma(h, h, h) : h2silu(h); }
+__device__ __forceinline__ uint32_t h2silu_e(uint32_t h) { return (EWS_EXP & 64) ? h2fma(h, h, h) : h2silu(h); }
 
 struct Params {
   int ntiles;
@@ -440,10 +443,10 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
         const uint32_t sa = soff[i] + (uint32_t)kb * S_KBLK;
         const uint4 hb = lds128(sa);
         uint4 o;
-        o.x = h2silu(h2add(h2add(g.a.x, hb.x), h2fma(rad, wr.x, h2add(g.td[i].x, g.to[i].x))));
-        o.y = h2silu(h2add(h2add(g.a.y, hb.y), h2fma(rad, wr.y, h2add(g.td[i].y, g.to[i].y))));
-        o.z = h2silu(h2add(h2add(g.a.z, hb.z), h2fma(rad, wr.z, h2add(g.td[i].z, g.to[i].z))));
-        o.w = h2silu(h2add(h2add(g.a.w, hb.w), h2fma(rad, wr.w, h2add(g.td[i].w, g.to[i].w))));
+        o.x = h2silu_p(h2add(h2add(g.a.x, hb.x), h2fma(rad, wr.x, h2add(g.td[i].x, g.to[i].x))));
+        o.y = h2silu_p(h2add(h2add(g.a.y, hb.y), h2fma(rad, wr.y, h2add(g.td[i].y, g.to[i].y))));
+        o.z = h2silu_p(h2add(h2add(g.a.z, hb.z), h2fma(rad, wr.z, h2add(g.td[i].z, g.to[i].z))));
+        o.w = h2silu_p(h2add(h2add(g.a.w, hb.w), h2fma(rad, wr.w, h2add(g.td[i].w, g.to[i].w))));
         sts128(sa, o);
       }
     };
@@ -648,16 +651,16 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
           }
           const uint32_t w0 = half ? ww.z : ww.x, w1 = half ? ww.w : ww.y;
 #if EWS_BIAS_MMA
-          const uint32_t x00 = h2silu(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])));
-          const uint32_t x10 = h2silu(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])));
-          const uint32_t x01 = h2silu(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])));
-          const uint32_t x11 = h2silu(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])));
+          const uint32_t x00 = h2silu_e(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])));
+          const uint32_t x10 = h2silu_e(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])));
+          const uint32_t x01 = h2silu_e(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])));
+          const uint32_t x11 = h2silu_e(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])));
 #else
           const uint32_t b0 = half ? bb.z : bb.x, b1 = half ? bb.w : bb.y;
-          const uint32_t x00 = h2silu(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), b0));
-          const uint32_t x10 = h2silu(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), b0));
-          const uint32_t x01 = h2silu(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), b1));
-          const uint32_t x11 = h2silu(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), b1));
+          const uint32_t x00 = h2silu_e(h2add(f2h2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), b0));
+          const uint32_t x10 = h2silu_e(h2add(f2h2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), b0));
+          const uint32_t x01 = h2silu_e(h2add(f2h2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), b1));
+          const uint32_t x11 = h2silu_e(h2add(f2h2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), b1));
 #endif
           m[(2 * hh) * 16 + 2 * jj] = x00; m[(2 * hh) * 16 + 2 * jj + 1] = x01;
           m[(2 * hh + 1) * 16 + 2 * jj] = x10; m[(2 * hh + 1) * 16 + 2 * jj + 1] = x11;
