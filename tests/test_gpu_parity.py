@@ -164,6 +164,42 @@ def test_forward_without_energy_head_equals_forward_with_it(n_rec, n_lig):
     assert torch.isfinite(a["energy"]).all()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("n_rec,n_lig", [(8, 4), (18, 1), (1, 25), (19, 1), (30, 29), (2, 2)])
+def test_tiny_complexes_vs_oracle(n_rec, n_lig, precision):
+    """Ragged small inputs (src/models/score_net_mlsb.py:89-94): N < 20 -> every residue is a neighbour and nothing is sampled,
+    20 <= N < 60 -> N - 20 sampled edges (K < 60, the tile's pad slots must stay silent), one-residue chains, and a batch
+    whose poses differ.  The CUDA forward on its own edges equals the oracle on the same edges."""
+    from dfmdock_b200.features import synthetic_complex
+    from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
+    from oracle import dfmdock_oracle as orc
+    sd, hp = synthetic_state_dict(1, 66), synthetic_hparams(66)
+    batch = synthetic_complex(n_rec, n_lig, seed=21)
+    batch["lig_pos"] = batch["lig_pos"] - torch.tensor([6.0, 0.0, 0.0])
+    N = n_rec + n_lig
+    model = _model(sd, hp, precision)
+    model.set_complex(batch)
+    g = torch.Generator().manual_seed(5)
+    lig = torch.stack([batch["lig_pos"] + torch.randn(1, 1, 3, generator=g) * 1.5 for _ in range(3)], 0)
+    t = torch.tensor([0.8, 0.5, 0.2])
+    out = model.score(lig, t, seed=7, forward_index=1, want_energy=True, return_edges=True)
+    K = min(N, 20) + (0 if N < 20 else min(N - 20, 40))
+    assert out["edges"].shape[-1] == K
+    net = orc.OracleNet(sd)
+    tol = TOL[precision]
+    for b in range(3):
+        e = out["edges"][b].cpu().long()
+        assert all(len(set(r.tolist())) == K for r in e), "duplicate neighbour"
+        if N <= 20:
+            assert all(sorted(r.tolist()) == list(range(N)) for r in e)
+        bb = dict(batch, lig_pos=lig[b], t=t[b:b + 1])
+        ref = net.forward(bb, edges=e)
+        for k in ("f", "tr_score", "rot_score"):
+            assert rel_err(out[k][b].cpu(), ref[k].reshape(out[k].shape[1:])) < tol["rel"], (k, b)
+        assert abs(float(out["energy"][b]) - float(ref["energy"])) < tol["energy"]
+        assert int(out["num_clashes"][b]) == int(ref["num_clashes"])
+
+
 def test_large_complex_beyond_1024_residues():
     """N = 1300 (> 1024: generic graph kernel, the 1N2C regime): kNN block equals the exact 20 nearest residues, 60 distinct
     neighbours per residue, finite scores, batched == single."""
