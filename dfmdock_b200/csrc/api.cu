@@ -21,10 +21,17 @@ void dfm_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* dfm_last_error(void) { return g_err; }
+// Programmatic dependent launch pays where a step is latency-bound and costs a little where every kernel fills the GPU
+// for long (measured on B200 at 2x150 residues, profiles/r02/pdl_by_batch.txt: 32 trajectories -6.5 %, 64 -1.7 %, 128 +0.7 %,
+// 256 +1.4 % step time with the attribute set), so by default it follows the size of the batch in flight (rows = B * N of
+// the last forward on this thread).  DFM_PDL=0 / 1 in the environment forces it off / on.
+static thread_local long long g_pdl_rows = 0;
+void dfm_pdl_set_rows(long long rows) { g_pdl_rows = rows; }
 bool dfm_pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("DFM_PDL"); on = e ? (atoi(e) != 0) : 1; }
-  return on != 0;
+  static int mode = -2;                  // -1: by batch size, 0 / 1: forced
+  if (mode == -2) { const char* e = getenv("DFM_PDL"); mode = e ? (atoi(e) != 0) : -1; }
+  if (mode >= 0) return mode != 0;
+  return g_pdl_rows <= DFM_PDL_MAX_ROWS;
 }
 extern "C" const char* dfm_version(void) { return "dfmdock_b200 0.1 (sm_100a)"; }
 
@@ -340,6 +347,7 @@ static int forward_impl(dfm_ctx* ctx, int B, const float* lig_pos, const float* 
   const bool want_energy = (flags & DFM_WANT_ENERGY) != 0;
   const int N = ctx->N, M = B * N;
   int rc;
+  dfm_pdl_set_rows(M);
   if ((rc = launch_prepare(ctx, B, lig_pos, ws, s))) return rc;
   if ((rc = launch_graph(ctx, B, (flags & DFM_GRAPH_GENERIC) != 0, edges, exp_noise, seed, stream_base, fwd_index, ws, s))) return rc;
   if (edges_out) {

@@ -57,12 +57,15 @@ __host__ inline bool dfm_once_per_device(unsigned long long& mask, int device) {
 // and blocks in pdl_wait() until the predecessor has completed and its writes are visible; pdl_trigger() at the top of a
 // kernel allows ITS successor to be scheduled as soon as SM resources free up.  Every kernel on the chain executes
 // pdl_wait() before it touches anything a predecessor wrote (or still reads), so completion order stays the stream order.
-// Without the launch attribute both instructions are no-ops.  DFM_PDL=0 in the environment disables the attribute.
+// Without the launch attribute both instructions are no-ops.  The attribute is set for batches of at most DFM_PDL_MAX_ROWS
+// residue rows (api.cu: dfm_pdl_enabled); DFM_PDL=0 / 1 in the environment forces it off / on.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
+constexpr long long DFM_PDL_MAX_ROWS = 28000;   // crossover between 64 x 300 (PDL faster) and 128 x 300 rows (PDL slower)
 bool dfm_pdl_enabled();
+void dfm_pdl_set_rows(long long rows);
 template <typename... KArgs, typename... Args>
 inline cudaError_t dfm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -123,6 +123,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_SKIP_PAD
 #define EWS_SKIP_PAD 1    // a producer warp whose second 4-row group lies entirely in the pad slots K..63 (warps 7 and 15 at K = 60)
 #endif                    // skips it; those rows keep the raw B_j the loaders staged (finite; their gate is 0)
+#ifndef EWS_WARP_ARRIVE
+#define EWS_WARP_ARRIVE 0   // 1: one mbarrier arrival per producer / epilogue WARP (fence or tcgen05 fence by every lane, __syncwarp, lane 0 arrives)
+#endif                      // instead of one per thread: 16 + 8 instead of 512 + 256 updates of the same barrier word per K block / tile
 #ifndef EWS_FOLD
 #define EWS_FOLD 16       // gate-logit products accumulated in half2 before they are folded to fp32: 4 (every column group), 8, 16 or 32
 #endif
@@ -145,6 +148,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrival of a whole warp whose lanes have each fenced their own writes / TMEM reads
+__device__ __forceinline__ void role_arrive(uint32_t bar, int lane) {
+#if EWS_WARP_ARRIVE
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+#else
+  mbar_arrive(bar);
+#endif
 }
 // try_wait parks the thread inside the instruction for a hardware-bounded time; between retries back off so that
 // waiting warps do not eat the issue slots of the working warps.  A lost arrival traps instead of hanging the GPU.
@@ -345,8 +357,8 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
   }
 #endif
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, NEPI * 32); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_full + 8 * i, EWS_WARP_ARRIVE ? NPROD : NPROD * 32); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, EWS_WARP_ARRIVE ? NEPI : NEPI * 32); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar_bfull + 8 * i, EWS_LOAD_BYKB ? 1 : EWS_NLOAD); mbar_init(bar_bready + 8 * i, 1); }
     tma_prefetch_desc(&tmB);
 #if EWS_BULK_W
@@ -484,24 +496,24 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
       issue(g1, mcur, ao, 1);
       TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 160u : 96u), par));
       compute(g0, mcur, 0);
-      fence_async_smem(); mbar_arrive(pbar + 0u);
+      fence_async_smem(); role_arrive(pbar + 0u, lane);
       // kb 1 (buffer 1); prefetch kb 2
       issue(g0, mcur, ao, 2);
       TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 168u : 104u), par));
       compute(g1, mcur, 1);
-      fence_async_smem(); mbar_arrive(pbar + 8u);
+      fence_async_smem(); role_arrive(pbar + 8u, lane);
       // kb 2 (buffer 0); prefetch kb 3
       issue(g1, mcur, ao, 3);
       TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 176u : 112u), par));
       compute(g0, mcur, 2);
-      fence_async_smem(); mbar_arrive(pbar + 16u);
+      fence_async_smem(); role_arrive(pbar + 16u, lane);
       // kb 3 (buffer 1); stage the next tile's metadata (its load has had three K blocks to land), prefetch its kb 0
       if (lane < 8) sts128(mnext + (uint32_t)lane * 16u, make_uint4(nm.x, nm.y, nm.z, nm.w));
       __syncwarp();
       if (has_next) issue(g0, mnext, aon, 0);
       TWAIT(tw0, mbar_wait<EWS_SLEEP_P>(pbar + (EWS_RELAY ? 184u : 120u), par));
       compute(g1, mcur, 3);
-      fence_async_smem(); mbar_arrive(pbar + 24u);
+      fence_async_smem(); role_arrive(pbar + 24u, lane);
     }
     if (EWS_TIMING && warp == 0 && lane == 0) { atomicAdd(p.timing + 0, tw0); atomicAdd(p.timing + 1, (unsigned long long)(clock64() - tstart)); }
   } else if (warp >= NPROD + NEPI) {
@@ -674,7 +686,7 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acce + 8 * buf);          // accumulator buffer may be overwritten by tile it + 2
+      role_arrive(bar_acce + 8 * buf, lane);    // accumulator buffer may be overwritten by tile it + 2
       // gate logit: sum over the 4 lanes of a row, then over the two column halves (shared memory)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

@@ -34,7 +34,7 @@ if os.path.exists(real):
         for k in ("f", "tr_score", "rot_score"):
             errs["real_" + k] = max(errs.get("real_" + k, 0), rel_err(out[k].cpu()[0], g[k].reshape(out[k].shape[1:])))
         errs["real_energy"] = max(errs.get("real_energy", 0), abs(float(out["energy"][0]) - float(g["energy"])))
-sd, hp, batch = make_workload()
+sd, hp, batch, _ = make_workload()
 model = Score_Model(sd, hp, precision="fp16").to("cuda")
 model.set_complex(batch)
 B = TRAJ_PER_GPU
