@@ -4,7 +4,7 @@ starts (t = 1.0, chains 50-150 A apart, radial up to 1e5 A^2); the free-running 
 live-reference goldens at far poses.
 
 Tolerances (SURVEY 8c protocol):
-  fp32 mode (FFMA kernels):                  5e-4 relative (L2) on f / tr_score / rot_score, 2e-3 absolute on energy
+  fp32 mode (FFMA kernels):                  1e-4 relative (L2) on f / tr_score / rot_score (measured worst 5.5e-5), 2e-3 absolute on energy
   fp16 mode (fp16 operands + fp16 SIMT, fp32 MMA accumulate): 1e-2 relative, 5e-2 absolute on energy per 10 units of |energy|
   T4 final pose: CA-RMSD <= 0.05 A in fp32 mode (the graph is injected, so no neighbour flips are possible)
 """
@@ -18,7 +18,7 @@ from util import load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 REAL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
-TOL = {"fp32": dict(rel=5e-4, energy=2e-3), "fp16": dict(rel=1e-2, energy=5e-2)}
+TOL = {"fp32": dict(rel=1e-4, energy=2e-3), "fp16": dict(rel=1e-2, energy=5e-2)}
 
 
 def _weights(kind):

@@ -1,7 +1,7 @@
 """GPU: the CUDA path (through the C ABI) against the oracle and the reference goldens.
 
 Tolerances (stated per mode):
-  fp32  (DFM_PRECISION_FP32, FFMA kernels):            5e-4 relative (L2) on f / scores / h, 2e-3 absolute on energy
+  fp32  (DFM_PRECISION_FP32, FFMA kernels):            1e-4 relative (L2) on f / scores / h (measured worst 5.5e-5), 2e-3 absolute on energy
   fp16  (default: fp16 tcgen05 operands + fp16 SIMT, fp32 MMA accumulate):  1e-2 relative (L2) on f / scores / h (SURVEY 8c's
         bound for the reduced-precision mode; measured worst 4.7e-3), 5e-2 absolute on energy
   integer outputs (bins, num_clashes, neighbour sets with injected noise): exact, except pair-feature bins whose
@@ -16,7 +16,7 @@ from util import FWD_CASES, case_small, load_golden, max_abs, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(rel=5e-4, energy=2e-3), "fp16": dict(rel=1e-2, energy=5e-2)}
+TOL = {"fp32": dict(rel=1e-4, energy=2e-3), "fp16": dict(rel=1e-2, energy=5e-2)}
 
 
 def _model(sd, hp, precision):
@@ -404,8 +404,8 @@ def test_score_along_reference_trajectory(precision):
     ts = torch.linspace(1.0, 1e-3, S)
     # after the first reverse step the synthetic score flings the ligand > 100 A away: radial ~ 1e5 A^2, so fp32 rounding of
     # radial*w1r inside u (shared with the reference) is amplified by the torque cross product (the per-residue forces are a
-    # near-pure translation there, so sum r x f cancels to ~1% of |r||f|) -> 8x looser than TOL (measured on B200: 2.0e-3 fp32)
-    tol = 8 * TOL[precision]["rel"]
+    # near-pure translation there, so sum r x f cancels to ~1% of |r||f|) -> 4e-3 in fp32 mode (measured on B200: 2.0e-3), 8e-2 in fp16 mode
+    tol = {"fp32": 4e-3, "fp16": 8e-2}[precision]
     for i in range(S + 1):
         t = ts[min(i, S - 1)]
         o = model.score(g["fwd_lig_pos"][i][None], t[None], edges=g["nbr"][i][None].int(), want_energy=(i == S))
