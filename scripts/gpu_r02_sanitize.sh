@@ -17,6 +17,13 @@ for (r, l, T) in ((25, 20, 3), (41, 31, 3), (150, 151, 3)):
     m.set_complex(bb)
     res = m.sample(bb["lig_pos"], T, num_steps=3, seed=1, use_clash_force=True, centre_mode=1)
     print(r, l, float(res["energy"].sum()))
+# tiny / ragged complexes: N < 20 (no sampled edges), one-residue chains
+for (r, l) in ((8, 4), (18, 1), (1, 25), (2, 2)):
+    bb = synthetic_complex(r, l, seed=21)
+    m.set_complex(bb)
+    o = m.score(bb["lig_pos"][None].repeat(3, 1, 1, 1).contiguous(), torch.tensor([0.8, 0.5, 0.2]), seed=7, forward_index=1, want_energy=True)
+    res = m.sample(bb["lig_pos"], 2, num_steps=2, seed=1, use_clash_force=True)
+    print("tiny", r, l, float(o["energy"].sum()), float(res["energy"].sum()))
 # fused last layer (needs >= 4 x SMs ligand tiles): 40 trajectories of 2 x 40 residues
 bb = synthetic_complex(40, 40, seed=3)
 bb["lig_pos"] = bb["lig_pos"] - torch.tensor([12.0, 0.0, 0.0])
@@ -39,5 +46,5 @@ print("sanitize script done")
 PY
 for tool in memcheck initcheck; do
   timeout 1200 compute-sanitizer --tool $tool --launch-timeout 0 --print-limit 10 python /tmp/san2.py > gpurun_out/sanitize_r02_$tool.log 2>&1; echo "$tool rc=$?"
-  grep -E "ERROR SUMMARY|Invalid|out of bounds|misaligned|Uninitialized|done|smoke ok|fused launches|N=1100" gpurun_out/sanitize_r02_$tool.log | sort | uniq -c | sort -rn | head -12
+  grep -E "ERROR SUMMARY|Invalid|out of bounds|misaligned|Uninitialized|done|smoke ok|fused launches|N=1100|tiny" gpurun_out/sanitize_r02_$tool.log | sort | uniq -c | sort -rn | head -12
 done
