@@ -41,11 +41,22 @@ def gather_rows(local, total, group=None):
 
 
 # ---- many complexes (BASELINE config #5): work items are (complex, trajectory); plan them over the ranks -----------------
-def complex_cost(n_res, num_samples):
-    """Relative cost of `num_samples` trajectories of an n_res-residue complex: the per-node work (edge / node kernels,
-    60 edges per residue) plus the O(N^2) stochastic-graph and energy scans, which take over above ~2000 residues
-    (profiles/r01/launches_1N2C_v9.csv: 26 % of a step at N = 2548)."""
-    return float(num_samples) * n_res * (1.0 + n_res / 6000.0)
+def _res_lig(size):
+    """sizes[c] is either the number of residues N or the pair (R, L); without L a third of the complex is assumed."""
+    if isinstance(size, (tuple, list)):
+        return int(size[0]) + int(size[1]), int(size[1])
+    return int(size), int(size) // 3
+
+
+def complex_cost(size, num_samples):
+    """Relative cost (in residue rows) of one launch sequence of `num_samples` trajectories of a complex (size = N or (R, L)):
+    a fixed part per work item (the latency-bound kernels of every lock-step step, set_complex, the copy back) + the
+    per-row work (edge / node kernels, 60 edges per residue; the ligand rows also pay the last layer and the coordinate
+    head) with the O(N^2) stochastic-graph scan on top.  Fitted to the measured device times of all 25 db5 complexes at
+    5 / 10 / 20 / 40 trajectories x 40 steps on one B200 (profiles/r02/c5_chunk_times.txt:
+    time = 9.8 ms + 2.92 us per row-equivalent, mean error 3.4 %, worst 7.4 %)."""
+    n, lig = _res_lig(size)
+    return 3400.0 + float(num_samples) * (n + 0.3 * lig) * (1.0 + n / 6000.0)
 
 
 def plan_work(sizes, num_samples, world, min_nodes=8192):
@@ -55,30 +66,59 @@ def plan_work(sizes, num_samples, world, min_nodes=8192):
     of poses per launch (40 trajectories on 8 GPUs = 5 per GPU: the kernels run far below their throughput), while
     whole complexes per rank cannot balance a set whose largest member is 13x its smallest.  So: a complex is cut
     into at most `world` contiguous trajectory chunks, only as many as keep `min_nodes` residues per launch and only
-    when its cost exceeds half a rank's share; chunks are then placed longest-first on the least-loaded rank.
-    Deterministic (every rank computes the same plan).  Returns a list of (complex index, lo, hi, rank) with the chunks
-    of a complex in trajectory order.
+    when its cost exceeds half a rank's share; chunks are placed longest-first on the least-loaded rank, each at the
+    cost of its own launch sequence (complex_cost: the fixed part is paid per chunk), and the placement is then refined
+    by moving or swapping single chunks off the most loaded rank for as long as that lowers the maximum load.
+    sizes[c] = residues of complex c, or the pair (R, L).  Deterministic (every rank computes the same plan).  Returns a
+    list of (complex index, lo, hi, rank) with the chunks of a complex in trajectory order.
     """
     if world <= 0:
         raise ValueError("world must be positive")
     costs = [complex_cost(n, num_samples) for n in sizes]
     share = sum(costs) / world if costs else 0.0
     chunks = []
-    for c, n in enumerate(sizes):
+    for c, size in enumerate(sizes):
+        n = _res_lig(size)[0]
         by_size = max(1, (num_samples * n) // max(1, min_nodes))
         by_cost = int(-(-costs[c] // max(share / 2.0, 1e-9))) if share > 0 else 1      # ceil
         parts = max(1, min(world, num_samples, by_size, by_cost))
         for r in range(parts):
             lo, hi = shard_range(num_samples, r, parts)
             if hi > lo:
-                chunks.append([c, lo, hi, costs[c] * (hi - lo) / num_samples])
+                chunks.append((c, lo, hi, complex_cost(size, hi - lo)))
+    chunks.sort(key=lambda ch: (-ch[3], ch[0], ch[1]))
     load = [0.0] * world
-    placed = []
-    for c, lo, hi, w in sorted(chunks, key=lambda ch: (-ch[3], ch[0], ch[1])):
+    owner = []
+    for c, lo, hi, w in chunks:
         r = min(range(world), key=lambda k: (load[k], k))
         load[r] += w
-        placed.append((c, lo, hi, r))
-    placed.sort()
+        owner.append(r)
+    # refinement: single moves / pairwise swaps off the most loaded rank (first improvement, fixed scan order)
+    for _ in range(8 * len(chunks) + 8):
+        hot = max(range(world), key=lambda k: (load[k], -k))
+        done = True
+        for i, (_, _, _, wi) in enumerate(chunks):
+            if owner[i] != hot:
+                continue
+            for r in sorted(range(world), key=lambda k: (load[k], k)):
+                if r == hot:
+                    continue
+                if max(load[r] + wi, load[hot] - wi) < load[hot] - 1e-9:                      # move i to r
+                    load[hot] -= wi; load[r] += wi; owner[i] = r
+                    done = False
+                    break
+                for j, (_, _, _, wj) in enumerate(chunks):
+                    if owner[j] == r and wj < wi and max(load[r] + wi - wj, load[hot] - wi + wj) < load[hot] - 1e-9:
+                        load[hot] += wj - wi; load[r] += wi - wj; owner[i], owner[j] = r, hot      # swap i and j
+                        done = False
+                        break
+                if not done:
+                    break
+            if not done:
+                break
+        if done:
+            break
+    placed = sorted((c, lo, hi, owner[i]) for i, (c, lo, hi, _) in enumerate(chunks))
     return placed
 
 

@@ -226,7 +226,7 @@ def run_planned(args, model, paths_list, embedder, device):
     (dfmdock_b200.distributed.plan_work), one object all-gather at the end, rank 0 computes the metrics and writes."""
     centre_mode = int(getattr(args, "centre_mode", 1))
     light = [load_inputs(p1, p2, id=id, parse_only=True) for id, p1, p2 in paths_list]
-    sizes = [len(r["receptor"]["seq"]) + len(r["ligand"]["seq"]) for r in light]
+    sizes = [(len(r["receptor"]["seq"]), len(r["ligand"]["seq"])) for r in light]      # (R, L): the planner's cost model uses both
 
     def loader(c):
         def load():

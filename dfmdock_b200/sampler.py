@@ -111,7 +111,7 @@ def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-
     """Many complexes x num_samples trajectories each (BASELINE config #5) over the ranks of `group`.
 
     loaders[c]() -> batch dict of complex c (called only on the ranks that own a chunk of it); sizes[c] = residues of
-    complex c (for the plan, dfmdock_b200.distributed.plan_work).  Trajectory k of every complex uses Philox subsequence
+    complex c, or the pair (R, L) (for the plan, dfmdock_b200.distributed.plan_work).  Trajectory k of every complex uses Philox subsequence
     k whatever the plan, so the result does not depend on the number of ranks; seeds[c] (default: `seed` for all) is the
     Philox key of complex c -- pass distinct values so that complexes do not share initial poses and noise.  One collective at the end: the chunks'
     result rows (pose, rot_update, tr_update, energy, num_clashes) are all-gathered as objects.

@@ -37,10 +37,10 @@ def main():
     paths = sorted(glob.glob(os.path.join(ref, "db5_all", "*.pt"))) or sorted(glob.glob(os.path.join(ref, "db5_*.pt")))
     ids = [os.path.splitext(os.path.basename(p))[0].replace("db5_", "") for p in paths]
     recs = [torch.load(p, weights_only=False) for p in paths]
-    sizes = [r["receptor"]["pos"].shape[0] + r["ligand"]["pos"].shape[0] for r in recs]
+    sizes = [(r["receptor"]["pos"].shape[0], r["ligand"]["pos"].shape[0]) for r in recs]      # (R, L) for the planner
     loaders = [(lambda r=r: batch_from_record(r, pos_width=model.pos_width, with_position_matrix=False)) for r in recs]
     # warm-up (allocator, module load) on the smallest complex
-    b0 = loaders[min(range(len(sizes)), key=lambda c: sizes[c])]()
+    b0 = loaders[min(range(len(sizes)), key=lambda c: sum(sizes[c]))]()
     model.set_complex(b0)
     model.sample(b0["lig_pos"], 2, num_steps=3, use_clash_force=True, centre_mode=1, seed=1)
     torch.cuda.synchronize()

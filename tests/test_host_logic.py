@@ -182,10 +182,14 @@ def test_inference_cli_surface_matches_reference_flags(tmp_path):
 
 
 def test_plan_work_covers_every_trajectory_once_and_balances():
-    """BASELINE config #5 planner: exact cover, deterministic, balanced, never more chunks than useful."""
+    """BASELINE config #5 planner: exact cover, deterministic, balanced, never more chunks than useful; sizes as N or as (R, L)."""
     from dfmdock_b200.distributed import complex_cost, plan_work
     db5 = [395, 695, 343, 456, 575, 626, 561, 2548, 329, 197, 352, 320, 430, 377, 430, 382, 339, 628, 404, 240, 535, 373, 588, 492, 214]
-    for sizes, T in ((db5, 40), ([197], 40), ([300, 300, 300], 7), ([2548], 3), ([], 40)):
+    db5_rl = [(223, 172), (368, 327), (242, 101), (311, 145), (470, 105), (426, 200), (432, 129), (2000, 548), (238, 91), (102, 95),
+              (223, 129), (195, 125), (269, 161), (170, 207), (355, 75), (275, 107), (275, 64), (574, 54), (263, 141), (120, 120),
+              (420, 115), (127, 246), (117, 471), (427, 65), (87, 127)]
+    assert [r + l for r, l in db5_rl] == db5
+    for sizes, T in ((db5, 40), (db5_rl, 40), ([197], 40), ([300, 300, 300], 7), ([2548], 3), ([], 40)):
         for world in (1, 2, 3, 8):
             plan = plan_work(sizes, T, world)
             assert plan == plan_work(sizes, T, world)
@@ -196,17 +200,21 @@ def test_plan_work_covers_every_trajectory_once_and_balances():
                 for k in range(lo, hi):
                     assert (c, k) not in seen
                     seen[(c, k)] = r
-                load[r] += complex_cost(sizes[c], T) * (hi - lo) / T
+                load[r] += complex_cost(sizes[c], hi - lo)
             assert len(seen) == len(sizes) * T
-            for c, n in enumerate(sizes):
+            for c, size in enumerate(sizes):
+                n = sum(size) if isinstance(size, tuple) else size
                 parts = [ch for ch in plan if ch[0] == c]
                 assert len(parts) <= max(1, min(world, T))
                 if len(parts) > 1:        # a complex is only cut when the pieces still fill a GPU
                     assert min(hi - lo for _, lo, hi, _ in parts) * n >= 8192 // 2
-            if sizes is db5 and world > 1:
-                assert max(load) <= 1.15 * sum(load) / world, (world, load)
+            if sizes in (db5, db5_rl) and world > 1:
+                assert max(load) <= 1.05 * sum(load) / world, (world, load)
     # small complexes stay whole: 40 trajectories x 197 residues is one launch-sized chunk
     assert len(plan_work([197, 214, 240], 40, 8)) == 3
+    # the ligand rows cost more than the receptor rows (last layer + coordinate head), the fixed part is paid per chunk
+    assert complex_cost((117, 471), 40) > complex_cost((471, 117), 40)
+    assert complex_cost(300, 10) + complex_cost(300, 30) > complex_cost(300, 40)
 
 
 _GLOO_SET_WORKER = r'''
