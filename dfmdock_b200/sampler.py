@@ -105,16 +105,64 @@ def sample_trajectories(model, batch, num_samples, num_steps=40, eps=1e-3, use_c
     return out
 
 
+_ROW_KEYS = ("lig_pos", "rot_update", "tr_update", "energy", "num_clashes")
+
+
+def _exchange_packed(done, plan, sizes, rank, world, group):
+    """One float32 all-gather of every rank's chunk results.  Layout of a rank's buffer: its chunks in plan order, each as
+    lig_pos [n, L, 3, 3] | rot_update [n, 3] | tr_update [n, 3] | energy [n] | num_clashes [n] (exact in float32 below 2^24).
+    -> [(c, lo, hi, dict of CPU tensors)] for ALL chunks, on every rank."""
+    import torch.distributed as dist
+
+    def numel(c, lo, hi):
+        return (hi - lo) * (int(sizes[c][1]) * 9 + 8)
+
+    per_rank = [[ch for ch in plan if ch[3] == r] for r in range(world)]
+    lens = [sum(numel(c, lo, hi) for c, lo, hi, _ in chs) for chs in per_rank]
+    mine = {(c, lo, hi): d for c, lo, hi, d in done}
+    dev = next((d["energy"].device for _, _, _, d in done), None)
+    if dev is None:       # a rank without work still takes part in the collective, on the model's device
+        dev = torch.device("cuda", torch.cuda.current_device()) if (world > 1 and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    flat = [t for c, lo, hi, _ in per_rank[rank] for t in
+            (mine[(c, lo, hi)][k].reshape(-1).to(torch.float32) for k in _ROW_KEYS)]
+    buf = torch.cat(flat) if flat else torch.zeros(0, device=dev)
+    if world > 1:
+        pad = torch.zeros(max(max(lens), 1), dtype=torch.float32, device=dev)
+        pad[: buf.numel()] = buf
+        allbuf = torch.empty(world * pad.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allbuf, pad, group=group)
+        allbuf = allbuf.view(world, -1).cpu()
+    else:
+        allbuf = buf.cpu()[None]
+    out = []
+    for r in range(world):
+        off = 0
+        for c, lo, hi, _ in per_rank[r]:
+            n, L = hi - lo, int(sizes[c][1])
+            row = allbuf[r]
+            d = {"lig_pos": row[off: off + n * L * 9].view(n, L, 3, 3).clone()}
+            off += n * L * 9
+            d["rot_update"] = row[off: off + 3 * n].view(n, 3).clone(); off += 3 * n
+            d["tr_update"] = row[off: off + 3 * n].view(n, 3).clone(); off += 3 * n
+            d["energy"] = row[off: off + n].clone(); off += n
+            d["num_clashes"] = row[off: off + n].round().to(torch.int32); off += n
+            out.append((c, lo, hi, d))
+    return out
+
+
 def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-3, use_clash_force=False,
                        noise_annealing=False, tr_noise_scale=0.5, rot_noise_scale=0.5, centre_mode=0, seed=0, ode=False,
-                       group=None, min_nodes=8192, seeds=None):
+                       group=None, min_nodes=8192, seeds=None, stats=None):
     """Many complexes x num_samples trajectories each (BASELINE config #5) over the ranks of `group`.
 
     loaders[c]() -> batch dict of complex c (called only on the ranks that own a chunk of it); sizes[c] = residues of
     complex c, or the pair (R, L) (for the plan, dfmdock_b200.distributed.plan_work).  Trajectory k of every complex uses Philox subsequence
     k whatever the plan, so the result does not depend on the number of ranks; seeds[c] (default: `seed` for all) is the
     Philox key of complex c -- pass distinct values so that complexes do not share initial poses and noise.  One collective at the end: the chunks'
-    result rows (pose, rot_update, tr_update, energy, num_clashes) are all-gathered as objects.
+    result rows (pose, rot_update, tr_update, energy, num_clashes) are all-gathered -- as one packed float32 tensor when sizes holds
+    (R, L) pairs (the rows then stay on the device until that point), as pickled objects otherwise.
+    stats: optional dict that receives this rank's wall-clock seconds per phase ("compute_s": its own chunks incl. loading the
+    records and the copies back, "gather_s": the collective, "assemble_s").
     Returns (results, plan): results[c] = dict of CPU tensors {lig_pos [T,L,3,3], rot_update [T,3], tr_update [T,3],
     energy [T], num_clashes [T], best} on every rank.
     """
@@ -124,6 +172,12 @@ def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-
     for c, lo, hi, r in plan:
         if r == rank:
             mine.setdefault(c, []).append((lo, hi))
+    import time
+    t0 = time.perf_counter()
+    # With (R, L) sizes every rank knows the shape of every chunk's result rows from the plan alone: the results then stay on
+    # the device (no per-chunk synchronisation, so loading the next record overlaps the running chunk) and travel in ONE
+    # packed float32 all-gather at the end.  With plain residue counts the rows are gathered as pickled objects.
+    packed = all(isinstance(sz, (tuple, list)) for sz in sizes)
     done = []
     for c in sorted(mine):
         batch = loaders[c]()
@@ -133,8 +187,15 @@ def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-
                                rot_noise_scale=rot_noise_scale, use_clash_force=use_clash_force,
                                noise_annealing=noise_annealing, centre_mode=centre_mode,
                                seed=seed if seeds is None else seeds[c], stream_base=lo, ode=ode)
-            done.append((c, lo, hi, {k: v.cpu() for k, v in res.items()}))
-    everything = [item for part in dist_utils.gather_objects(done, group) for item in part]
+            if packed and tuple(res["lig_pos"].shape[:2]) != (hi - lo, int(sizes[c][1])):
+                raise RuntimeError("sample_complex_set: complex %d returned poses %s, sizes says L = %d" % (c, tuple(res["lig_pos"].shape), sizes[c][1]))
+            done.append((c, lo, hi, res if packed else {k: v.cpu() for k, v in res.items()}))
+    t1 = time.perf_counter()
+    if packed:
+        everything = _exchange_packed(done, plan, sizes, rank, world, group)
+    else:
+        everything = [item for part in dist_utils.gather_objects(done, group) for item in part]
+    t2 = time.perf_counter()
     results = []
     for c in range(len(sizes)):
         parts = sorted((lo, hi, d) for cc, lo, hi, d in everything if cc == c)
@@ -144,4 +205,6 @@ def sample_complex_set(model, loaders, sizes, num_samples, num_steps=40, eps=1e-
         out = {k: torch.cat([d[k] for _, _, d in parts], dim=0) for k in parts[0][2]}
         out["best"] = int(torch.argmin(out["energy"]).item())
         results.append(out)
+    if stats is not None:
+        stats.update(compute_s=t1 - t0, gather_s=t2 - t1, assemble_s=time.perf_counter() - t2)
     return results, plan

@@ -49,7 +49,8 @@ def main():
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    results, plan = sample_complex_set(model, loaders, sizes, T, num_steps=S, use_clash_force=True, centre_mode=1, seed=42)
+    stats = {}
+    results, plan = sample_complex_set(model, loaders, sizes, T, num_steps=S, use_clash_force=True, centre_mode=1, seed=42, stats=stats)
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
@@ -60,7 +61,10 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     ms = float(ms)
+    from dfmdock_b200.distributed import gather_objects
+    all_stats = gather_objects({k: round(v * 1e3, 1) for k, v in stats.items()})
     if rank == 0:
+        print("per-rank phases (ms):", all_stats)
         rows = []
         for c, res in enumerate(results):
             rec = recs[c]

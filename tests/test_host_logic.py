@@ -231,14 +231,18 @@ class FakeModel:                        # stands in for the CUDA model: result r
         return {"lig_pos": (self.c * 1000 + k)[:, None, None, None].expand(n, 2, 3, 3).clone(), "rot_update": k[:, None].expand(n, 3).clone(),
                 "tr_update": k[:, None].expand(n, 3).clone(), "energy": -((k - 3 - self.c) ** 2), "num_clashes": torch.zeros(n, dtype=torch.int32)}
 
-sizes = [900, 200, 2500, 300]
 loaders = [(lambda c=c: {"c": c, "lig_pos": torch.zeros(2, 3, 3)}) for c in range(4)]
-results, plan = sampler.sample_complex_set(FakeModel(), loaders, sizes, 12, num_steps=2, min_nodes=2048)
-assert {r for _, _, _, r in plan} == {0, 1}, plan
-for c, res in enumerate(results):
-    assert res["lig_pos"].shape == (12, 2, 3, 3)
-    assert torch.equal(res["lig_pos"][:, 0, 0, 0], c * 1000 + torch.arange(12, dtype=torch.float32)), (c, res["lig_pos"][:, 0, 0, 0])
-    assert res["best"] == int(torch.argmin(res["energy"]))
+# residue counts -> rows gathered as objects; (R, L) pairs -> one packed float32 all-gather; one complex only -> a rank without work
+for sizes in ([900, 200, 2500, 300], [(898, 2), (198, 2), (2498, 2), (298, 2)], [(198, 2)]):
+    results, plan = sampler.sample_complex_set(FakeModel(), loaders[:len(sizes)], sizes, 12, num_steps=2, min_nodes=2048)
+    assert len(sizes) == 1 or {r for _, _, _, r in plan} == {0, 1}, plan
+    assert len(results) == len(sizes)
+    for c, res in enumerate(results):
+        assert res["lig_pos"].shape == (12, 2, 3, 3)
+        assert torch.equal(res["lig_pos"][:, 0, 0, 0], c * 1000 + torch.arange(12, dtype=torch.float32)), (c, res["lig_pos"][:, 0, 0, 0])
+        assert torch.equal(res["rot_update"][:, 2], torch.arange(12, dtype=torch.float32))
+        assert res["num_clashes"].dtype == torch.int32 and res["energy"].shape == (12,)
+        assert res["best"] == int(torch.argmin(res["energy"]))
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
