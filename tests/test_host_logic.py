@@ -217,6 +217,45 @@ def test_plan_work_covers_every_trajectory_once_and_balances():
     assert complex_cost(300, 10) + complex_cost(300, 30) > complex_cost(300, 40)
 
 
+def test_plan_work_against_measured_chunk_times():
+    """The planner's cost model against the device times measured on B200 for every db5 complex at 40 / 20 / 10 / 5 trajectories
+    (profiles/r02/c5_chunk_times.txt): the model is within 10 % of every measurement, and the 8-rank plan's busiest rank, priced
+    with the MEASURED times, stays within 6 % of a perfect split."""
+    import re
+    from dfmdock_b200.distributed import complex_cost, plan_work
+    rl = {"1AVX": (223, 172), "1H1V": (368, 327), "1HCF": (242, 101), "1IRA": (311, 145), "1JIW": (470, 105), "1JPS": (426, 200),
+          "1MLC": (432, 129), "1N2C": (2000, 548), "1NW9": (238, 91), "1QA9": (102, 95), "1VFB": (223, 129), "1ZHI": (195, 125),
+          "2A1A": (269, 161), "2A9K": (170, 207), "2AYO": (355, 75), "2SIC": (275, 107), "2SNI": (275, 64), "2VDB": (574, 54),
+          "3SZK": (263, 141), "4POU": (120, 120), "5C7X": (420, 115), "5HGG": (127, 246), "5JMO": (117, 471), "6B0S": (427, 65),
+          "7CEI": (87, 127)}
+    ids, times = [], {}
+    with open(os.path.join(ROOT, "profiles", "r02", "c5_chunk_times.txt")) as f:
+        for line in f:
+            m = re.match(r"CHUNK (\S+) N=(\d+)", line)
+            if m:
+                ids.append(m.group(1))
+                assert sum(rl[m.group(1)]) == int(m.group(2))
+                times[m.group(1)] = {int(t): float(ms) for t, ms in re.findall(r"T=(\d+) ([\d.]+) ms", line)}
+    assert len(ids) == 25
+    ms_per_unit = 2.924e-3                       # the fit: time = ms_per_unit * complex_cost (9.8 ms fixed + 2.92 us per row-equivalent)
+    for cid in ids:
+        for t, ms in times[cid].items():
+            assert abs(ms_per_unit * complex_cost(rl[cid], t) - ms) <= 0.10 * ms, (cid, t, ms)
+
+    def measured(cid, n):                        # affine in the trajectory count between / beyond the measured points
+        pts = sorted(times[cid].items())
+        (t0, m0), (t1, m1) = (pts[0], pts[1]) if n <= pts[1][0] else next((a, b) for a, b in zip(pts, pts[1:]) if n <= b[0])
+        return m0 + (m1 - m0) * (n - t0) / (t1 - t0)
+
+    sizes = [rl[c] for c in ids]
+    total = sum(times[c][40] for c in ids)
+    for world, bound in ((2, 1.03), (4, 1.04), (8, 1.06)):
+        load = [0.0] * world
+        for c, lo, hi, r in plan_work(sizes, 40, world):
+            load[r] += measured(ids[c], hi - lo)
+        assert max(load) <= bound * total / world, (world, [round(x) for x in load], total / world)
+
+
 _GLOO_SET_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["DFM_ROOT"])
