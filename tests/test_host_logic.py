@@ -22,6 +22,36 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.dfm_version()
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/dfmdock_b200.h compiles as C99 and as C++11 with -Wall -Wextra -pedantic, and a
+    plain-C consumer links against the library and calls entry points that need no GPU (no torch types anywhere)."""
+    import shutil
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    from dfmdock_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "consumer.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "dfmdock_b200.h"\n'
+                   'int main(void) {\n'
+                   '  if (!dfm_version() || !strstr(dfm_version(), "sm_100a")) return 1;\n'
+                   '  if (dfm_set_weight(NULL, "x", NULL, NULL, 0) == 0) return 2;      /* a null context is an error, not a crash */\n'
+                   '  if (!dfm_last_error() || !dfm_last_error()[0]) return 3;\n'
+                   '  if (dfm_metrics_workspace_bytes(100, 90) == 0) return 4;\n'
+                   '  printf("%s\\n", dfm_version());\n  return 0;\n}\n')
+    cpp = tmp_path / "consumer.cpp"
+    cpp.write_text('#include "dfmdock_b200.h"\nint main() { return dfm_version() ? 0 : 1; }\n')
+    flags = ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc]
+    subprocess.run([gcc, "-std=c99"] + flags + ["-fsyntax-only", str(src)], check=True)
+    subprocess.run([gxx, "-std=c++11"] + flags + ["-fsyntax-only", str(cpp)], check=True)
+    exe = tmp_path / "consumer"
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldfmdock_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "dfmdock_b200" in out.stdout
+
+
 def test_no_cpu_fallback_and_product_never_imports_oracle():
     from dfmdock_b200 import Score_Model
     from dfmdock_b200.synthetic import synthetic_hparams, synthetic_state_dict
