@@ -123,6 +123,9 @@ static_assert(NPROD * PROD_REGS + NEPI * EPI_REGS + 4 * MMA_REGS <= (NPROD + NEP
 #ifndef EWS_SKIP_PAD
 #define EWS_SKIP_PAD 1    // a producer warp whose second 4-row group lies entirely in the pad slots K..63 (warps 7 and 15 at K = 60)
 #endif                    // skips it; those rows keep the raw B_j the loaders staged (finite; their gate is 0)
+#ifndef EWS_TABLE_NOALLOC
+#define EWS_TABLE_NOALLOC 0   // 1: the producers' table-row gathers bypass L1 allocation (ld.global.nc.L1::no_allocate)
+#endif
 #ifndef EWS_WARP_ARRIVE
 #define EWS_WARP_ARRIVE 0   // 1: one mbarrier arrival per producer / epilogue WARP (fence or tcgen05 fence by every lane, __syncwarp, lane 0 arrives)
 #endif                      // instead of one per thread: 16 + 8 instead of 512 + 256 updates of the same barrier word per K block / tile
@@ -232,6 +235,15 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ float ldsf(uint32_t a) { return __uint_as_float(lds32(a)); }
 __device__ __forceinline__ void stsf(uint32_t a, float v) { sts32(a, __float_as_uint(v)); }
 
+__device__ __forceinline__ uint4 ldg_table(const void* p) {
+#if EWS_TABLE_NOALLOC
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const uint4*>(p));
+#endif
+}
 // ---- packed half2 helpers on raw 32-bit registers ---------------------------------------------------
 __device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b) {
   uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
@@ -441,9 +453,9 @@ __device__ __forceinline__ void edge_body(const Params& p, const CUtensorMap& tm
         if (i == 1 && !full) break;
         uint4 mt = lds128(mslot + mlane + (uint32_t)(4 * i) * 16u);
         if (EWS_EXP & 2) { mt.y = 0; mt.z = ((int)mt.z >= 0) ? 0u : mt.z; }
-        g.td[i] = __ldg(reinterpret_cast<const uint4*>(tdrp_l + (size_t)mt.y * H + kb * 64));
+        g.td[i] = ldg_table(tdrp_l + (size_t)mt.y * H + kb * 64);
         g.to[i] = make_uint4(0, 0, 0, 0);
-        if ((int)mt.z >= 0) g.to[i] = __ldg(reinterpret_cast<const uint4*>(totp_l + (size_t)mt.z * H + kb * 64));
+        if ((int)mt.z >= 0) g.to[i] = ldg_table(totp_l + (size_t)mt.z * H + kb * 64);
       }
     };
     auto compute = [&](const GBuf& g, uint32_t mslot, int kb) {
